@@ -1,0 +1,166 @@
+/*
+ * prim3d_b200.h -- C ABI of the B200-native marching cubes / marching tetrahedra hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * names the reference interface it replaces (paths relative to lzhnb/Primitive3D @ 56af21e).
+ * The reference-facing module prim3d.libPrim3D (primitive3d_b200/csrc/bindings.cpp) is a thin
+ * pybind11 layer over these calls; INTEGRATION.md shows the binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - all `grid`, `workspace`, output and table pointers are DEVICE pointers on the current
+ *     CUDA device unless a parameter is documented as host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns a p3d_status; p3d_last_error() gives the message of the last
+ *     failure on the calling thread;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     P3D_ERR_CUDA.
+ */
+#ifndef PRIM3D_B200_H_
+#define PRIM3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_ABI_VERSION 1
+
+typedef enum p3d_status {
+    P3D_OK = 0,
+    P3D_ERR_INVALID = 1,   /* bad argument (null pointer, non-positive size, ...)          */
+    P3D_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed                   */
+    P3D_ERR_OVERFLOW = 3,  /* the vertex count does not fit the int32 face-index contract   */
+    P3D_ERR_WORKSPACE = 4  /* the workspace passed is smaller than *_workspace_bytes()      */
+} p3d_status;
+
+int p3d_abi_version(void);
+const char *p3d_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense-grid marching cubes.
+ * Replaces prim3d::marching_cubes, src/prim3d/Utility/marching_cubes.h:14-15 and
+ * marching_cubes.cu:212-305 (count_vertices_faces_kernel :4-68, gen_vertices_kernel :70-138,
+ * gen_faces_kernel :140-209, bounding-box epilogue :289-298).
+ *
+ * The grid is float32, C-contiguous, idx = i*(ry*rz) + j*rz + k (marching_cubes.cu:20).
+ * A sample is inside iff value > thresh (NaN and == thresh are outside).
+ *
+ * The reference needs the output sizes before it can allocate, and so do we; the call is
+ * therefore split at the same place the reference synchronises (marching_cubes.cu:251-252):
+ *
+ *   p3d_mc_count()  classifies the grid once, builds the compact side products in the
+ *                   workspace, and returns {V, F} to the host (one stream synchronise);
+ *   p3d_mc_emit()   writes vertices float32 [V,3] and faces int32 [F,3] into caller-owned
+ *                   buffers (asynchronous on `stream`).
+ *
+ * Output order is deterministic: vertices are numbered row by row ((x,y) rows in C order;
+ * inside a row all x-edge vertices by z, then y-edge, then z-edge vertices), faces are in
+ * voxel-major cell order with the triangle-table order inside a cell.  The reference's own
+ * order is atomicAdd-arbitrary (marching_cubes.cu:104,117,130,199).
+ *
+ * Slab decomposition (multi-GPU, dim 0): `rx` planes are present in memory, the first
+ * `owned_x` of them are owned by this call, a trailing plane (rx == owned_x + 1) is a halo
+ * owned by the next shard.  `x_origin` is the global index of local plane 0 and `global_rx`
+ * the full-grid Rx used by the bounding-box scale.  Single GPU: owned_x = global_rx = rx,
+ * x_origin = 0.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct p3d_mc_desc {
+    int64_t rx, ry, rz;  /* planes/rows/samples present in `grid`                            */
+    int64_t owned_x;     /* leading planes owned by this call: rx, or rx-1 with a halo plane */
+    int64_t x_origin;    /* global dim-0 index of local plane 0                              */
+    int64_t global_rx;   /* full-grid Rx (bounding-box scale, marching_cubes.cu:294)         */
+    float thresh;
+    float lower[3];      /* bounding box, marching_cubes.cu:290-297 (host values)            */
+    float upper[3];
+} p3d_mc_desc;
+
+/* Bytes of device workspace p3d_mc_count/p3d_mc_emit need for this descriptor
+ * (1 bit per sample + 24 bytes per (x,y) row + scan state).  0 on invalid descriptor. */
+size_t p3d_mc_workspace_bytes(const p3d_mc_desc *desc);
+
+/* counts_host[0] = V (vertices owned by this shard), counts_host[1] = F (faces of its cells).
+ * Host memory.  Synchronises `stream`.  P3D_ERR_OVERFLOW if V > INT32_MAX. */
+p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace,
+                        size_t workspace_bytes, int64_t *counts_host, void *stream);
+
+/* vertices: float[3*V], faces: int32[3*F] (device).  Face indices are written as
+ * vertex_id_base + local id (vertex_id_base = exclusive prefix of V over lower shards;
+ * 0 on a single GPU).  Must follow p3d_mc_count on the same workspace and grid. */
+p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *workspace,
+                       float *vertices, int32_t *faces, int64_t vertex_id_base, void *stream);
+
+/* Multi-GPU halo exchange of vertex numbering (16 bytes per row of one plane):
+ * export copies the row table of local plane 0 into table_out (uint32[4*ry], device);
+ * import installs the next shard's exported table as the numbering of this shard's halo
+ * plane, shifted by `delta` = this shard's V.  Both asynchronous on `stream`. */
+p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *workspace,
+                                     uint32_t *table_out, void *stream);
+p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace,
+                                    const uint32_t *table_in, int64_t delta, void *stream);
+
+/* One-shot convenience for C/C++ callers: count, allocate through the callback, emit.
+ * alloc(ctx, bytes) must return device memory on the current device (or NULL). */
+typedef void *(*p3d_alloc_fn)(void *ctx, size_t bytes);
+p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn alloc, void *alloc_ctx,
+                      float **vertices, int32_t **faces, int64_t *num_vertices, int64_t *num_faces,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Marching tetrahedra.
+ * Replaces prim3d/utility/marching_tetrahedras.py:89-235 (a chain of ~25 torch ops in the
+ * reference: gather, torch.det, torch.unique(dim=0), masked scatter, gathers).
+ *
+ * points float32 [P,3], tets int64 [T,4] (MUTATED IN PLACE like the reference, :148: columns
+ * 0 and 1 of negatively oriented tets are swapped), sdf float32 [P]; occupancy is sdf > 0.
+ * Outputs follow the reference exactly: vertex i is the i-th crossing edge in lexicographic
+ * (min id, max id) order (the order torch.unique(dim=0) defines, :157-173), interpolated as
+ * p0*w0 + p1*w1 with w = (-s1, s0)/(s0 - s1) (:177-189); faces int64 [F,3] list all
+ * one-triangle tets first, then all two-triangle tets (:205-223); tet_idx int64 [F] is the
+ * source tet of each face (:225-234).
+ *
+ * Output sizes are data dependent twice over (F after classification, V after the edges are
+ * de-duplicated), so the call is split in three; the first two synchronise `stream`:
+ *
+ *   p3d_mt_classify()  orientation fix (in place), occupancy code per tet -> codes[T];
+ *                      counts_host = {n1, n2, ne}: tets with one / two triangles and the
+ *                      number of crossing-edge instances.  F = n1 + 2*n2.
+ *   p3d_mt_index()     compacts the valid tets in order, sorts and de-duplicates the crossing
+ *                      edges (hand-written LSD radix sort + look-back scans);
+ *                      counts_host = {V}.
+ *   p3d_mt_emit()      verts float32 [V,3], edges int64 [V,2] (the (min,max) point ids each
+ *                      vertex interpolates, needed by the backward), faces int64 [F,3],
+ *                      tet_idx int64 [F].  Asynchronous.
+ * ---------------------------------------------------------------------------------------- */
+/* Bytes of the device buffer `codes` (one byte per tet plus the classify counters). */
+size_t p3d_mt_codes_bytes(int64_t num_tets);
+
+p3d_status p3d_mt_classify(const float *points, int64_t num_points, int64_t *tets, int64_t num_tets,
+                           const float *sdf, uint8_t *codes, int64_t *counts_host, void *stream);
+
+/* Bytes of device workspace p3d_mt_index / p3d_mt_emit need, from p3d_mt_classify's counts. */
+size_t p3d_mt_workspace_bytes(int64_t num_tets, int64_t n1, int64_t n2, int64_t ne);
+
+p3d_status p3d_mt_index(const int64_t *tets, int64_t num_tets, int64_t num_points, const float *sdf,
+                        const uint8_t *codes, int64_t n1, int64_t n2, int64_t ne, void *workspace,
+                        size_t workspace_bytes, int64_t *counts_host, void *stream);
+
+/* edges and tet_idx may be NULL. */
+p3d_status p3d_mt_emit(const float *points, const int64_t *tets, int64_t num_tets, const float *sdf,
+                       const uint8_t *codes, int64_t n1, int64_t n2, int64_t ne, int64_t num_vertices,
+                       const void *workspace, float *verts, int64_t *edges, int64_t *faces,
+                       int64_t *tet_idx, void *stream);
+
+/* Backward of the vertex interpolation (the reference's verts are differentiable w.r.t.
+ * points and sdf, marching_tetrahedras.py:175-189): accumulates into grad_points [P,3] and
+ * grad_sdf [P] (both pre-zeroed by the caller) from grad_verts [V,3] and edges [V,2]. */
+p3d_status p3d_mt_backward(const float *points, const float *sdf, const int64_t *edges,
+                           int64_t num_vertices, const float *grad_verts, float *grad_points,
+                           float *grad_sdf, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIM3D_B200_H_ */

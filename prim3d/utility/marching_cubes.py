@@ -1,0 +1,108 @@
+"""Python entry points of the marching-cubes path: `marching_cubes`, `save_mesh`.
+
+Host-side mirror of the reference's prim3d/utility/marching_cubes.py (`scale_to_bound` :10-31,
+`marching_cubes` :34-98, `save_mesh` :100-141): same names, argument meaning, return types and
+error behaviour, so the reference's examples run unchanged.  The CUDA work happens in
+`prim3d.libPrim3D.marching_cubes` (primitive3d_b200/csrc).
+
+One deliberate difference, required by this repository's "no CPU fallback" rule: the reference
+silently switches to the third-party `mcubes` package when CUDA is unavailable (:64); here that
+only happens when the caller asks for it with `cpu=True`, and a missing CUDA device is an error.
+"""
+from pathlib import Path
+
+import numpy as np
+import torch
+
+import prim3d.libPrim3D as _C
+
+_SEQ = (list, tuple, np.ndarray, torch.Tensor)
+
+
+def scale_to_bound(scale):
+    """Bounding box (lower, upper) from the `scale` argument (reference :10-31):
+    float s -> [0,0,0],[s,s,s]; length-3 -> [0,0,0],scale; length-2 of floats (lo, hi) ->
+    [lo]*3,[hi]*3; length-2 of length-3 sequences -> (scale[0], scale[1]); else TypeError."""
+    if isinstance(scale, float):
+        return [0.0] * 3, [scale] * 3
+    if not isinstance(scale, _SEQ):
+        raise TypeError()
+    if len(scale) == 3:
+        return [0.0] * 3, list(scale)
+    if len(scale) == 2:
+        lo, hi = scale[0], scale[1]
+        if isinstance(lo, float):
+            return [lo] * 3, [hi] * 3
+        assert len(lo) == len(hi) == 3
+        return list(lo), list(hi)
+    raise TypeError()
+
+
+def marching_cubes(density_grid, thresh, scale=None, verbose=False, cpu=False):
+    """Extract the `thresh` iso-surface of a dense grid.
+
+    Args:
+        density_grid: torch.Tensor or np.ndarray [Rx, Ry, Rz], any dtype (cast to float32).
+        thresh: iso value; a sample is inside iff value > thresh.
+        scale: None (bounding box [0, shape]), or anything `scale_to_bound` accepts.
+        verbose: print `#vertices=` / `#triangles=`.
+        cpu: use the third-party `mcubes` package instead (float64 vertices, int64 faces).
+    Returns:
+        (vertices float32 [V,3], faces int32 [F,3]) on the CUDA device.
+    """
+    if scale is None:
+        lower = [0.0, 0.0, 0.0]
+        upper = [density_grid.shape[0], density_grid.shape[1], density_grid.shape[2]]
+    else:
+        lower, upper = scale_to_bound(scale)
+
+    if cpu:
+        try:
+            import mcubes
+        except Exception:
+            raise ImportError("the cpu mode cumcubes is the wrapper of `mcubes`, please install the mcubes")
+        volume = density_grid.detach().cpu().numpy() if isinstance(density_grid, torch.Tensor) \
+            else np.asarray(density_grid)
+        vertices, faces = mcubes.marching_cubes(volume, thresh)
+        # the reference divides by the scale here (:76-78); kept because it is observable
+        box = (np.array(upper) - np.array(lower)) / np.array(volume.shape)
+        vertices = torch.tensor(vertices / box + np.array(lower))
+        faces = torch.tensor(faces.astype(np.int64))
+    else:
+        if not torch.cuda.is_available():
+            raise RuntimeError("prim3d.marching_cubes needs a CUDA device (pass cpu=True for the mcubes wrapper)")
+        if isinstance(density_grid, np.ndarray):
+            density_grid = torch.tensor(density_grid)
+        density_grid = density_grid.cuda().to(torch.float32)
+        if min(density_grid.shape[0], density_grid.shape[1], density_grid.shape[2]) < 2:
+            raise ValueError()
+        vertices, faces = _C.marching_cubes(density_grid.contiguous(), thresh,
+                                            [float(v) for v in lower], [float(v) for v in upper])
+
+    if verbose:
+        print(f"#vertices={vertices.shape[0]}")
+        print(f"#triangles={faces.shape[0]}")
+    return vertices, faces
+
+
+def save_mesh(vertices, faces, colors=None, filename="temp.ply", verbose=False):
+    """Write a binary PLY (reference :100-141): faces are cast to int32, colors default to 127
+    and are cast to uint8; any extension other than `.ply` raises NotImplementedError."""
+    if isinstance(filename, Path):
+        filename = str(filename)
+    if isinstance(vertices, np.ndarray):
+        vertices = torch.tensor(vertices)
+    if isinstance(faces, np.ndarray):
+        faces = torch.tensor(faces)
+    faces = faces.int()
+    if colors is None:
+        colors = torch.ones_like(vertices) * 127
+    elif isinstance(colors, np.ndarray):
+        colors = torch.tensor(colors)
+    colors = colors.to(torch.uint8)
+
+    if not filename.endswith(".ply"):
+        raise NotImplementedError()
+    _C.save_mesh_as_ply(filename, vertices, faces, colors)
+    if verbose:
+        print(f"save as {filename} successfully!")

@@ -1,0 +1,64 @@
+"""`prim3d.marching_tetrahedras` -- same signature and outputs as the reference's
+prim3d/utility/marching_tetrahedras.py:89-235, computed by hand-written sm_100a kernels
+(primitive3d_b200/csrc/mt_kernels.cu) instead of ~25 torch ops.
+
+Contract kept from the reference:
+  * `tets` is MUTATED IN PLACE: columns 0 and 1 of negatively oriented tets are swapped (:148);
+  * occupancy is `sdf > 0`; vertex i is the i-th crossing edge in lexicographic (min, max) order
+    (the order `torch.unique(dim=0)` defines, :157-173); positions are p0*w0 + p1*w1 with
+    w = (-s1, s0) / (s0 - s1) (:177-189);
+  * faces are int64, all one-triangle tets first, then all two-triangle tets (:205-223);
+  * outputs live on the inputs' device; `verts` is differentiable w.r.t. `vertices` and `sdf`
+    (the reference leaves :175-189 outside no_grad).
+
+There is one compute path, the CUDA one.  CPU tensors (examples/sphere_tetrahedra.py:15-16 calls
+with CPU tensors first) are staged through the GPU and the results copied back, including the
+in-place flip of `tets`; without a CUDA device the call fails.
+"""
+import torch
+
+import prim3d.libPrim3D as _C
+
+
+class _MarchingTets(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, sdf, tets):
+        verts, faces, tet_idx, edges = _C.marching_tetrahedras(points, tets, sdf)
+        ctx.save_for_backward(points, sdf, edges)
+        ctx.mark_non_differentiable(faces, tet_idx, edges)
+        return verts, faces, tet_idx, edges
+
+    @staticmethod
+    def backward(ctx, grad_verts, _gf, _gt, _ge):
+        points, sdf, edges = ctx.saved_tensors
+        grad_points, grad_sdf = _C.marching_tetrahedras_backward(points, sdf, edges, grad_verts.contiguous())
+        return grad_points, grad_sdf, None
+
+
+def marching_tetrahedras(vertices, tets, sdf, return_tet_idx=False):
+    """vertices float32 [P,3], tets int64 [T,4] (mutated), sdf float32 [P]
+    -> (verts float32 [V,3], faces int64 [F,3][, tet_idx int64 [F]])."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("prim3d.marching_tetrahedras needs a CUDA device")
+    home = vertices.device
+    staged = not vertices.is_cuda
+    points_d = vertices.cuda() if staged else vertices
+    sdf_d = sdf.to(points_d.device)
+    tets_d = tets.to(points_d.device)
+    if tets_d.dtype != torch.int64:
+        raise TypeError("tets must be int64")
+    if not tets_d.is_contiguous():
+        tets_d = tets_d.contiguous()
+    points_d = points_d.to(torch.float32).contiguous()
+    sdf_d = sdf_d.to(torch.float32).contiguous()
+
+    verts, faces, tet_idx, _ = _MarchingTets.apply(points_d, sdf_d, tets_d)
+
+    if tets_d.data_ptr() != tets.data_ptr():
+        with torch.no_grad():
+            tets.copy_(tets_d)  # the caller's tensor sees the orientation fix, like the reference
+    if staged:
+        verts, faces, tet_idx = verts.to(home), faces.to(home), tet_idx.to(home)
+    if return_tet_idx:
+        return verts, faces, tet_idx
+    return verts, faces

@@ -1,0 +1,165 @@
+"""ctypes bindings of include/prim3d_b200.h over torch CUDA tensors.
+
+This is the C-ABI call path the parity tests use (`tests/ -m gpu`) and the one the multi-GPU
+driver (sharded.py) is built on.  torch is used for device memory and streams only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprim3d_b200.so")
+_lib = None
+
+P3D_OK, P3D_ERR_INVALID, P3D_ERR_CUDA, P3D_ERR_OVERFLOW, P3D_ERR_WORKSPACE = range(5)
+
+
+class McDesc(ctypes.Structure):
+    """struct p3d_mc_desc (include/prim3d_b200.h)."""
+    _fields_ = [("rx", ctypes.c_int64), ("ry", ctypes.c_int64), ("rz", ctypes.c_int64),
+                ("owned_x", ctypes.c_int64), ("x_origin", ctypes.c_int64), ("global_rx", ctypes.c_int64),
+                ("thresh", ctypes.c_float), ("lower", ctypes.c_float * 3), ("upper", ctypes.c_float * 3)]
+
+    @classmethod
+    def make(cls, shape, thresh, lower=None, upper=None, owned_x=None, x_origin=0, global_rx=None):
+        rx, ry, rz = (int(s) for s in shape)
+        global_rx = rx if global_rx is None else int(global_rx)
+        lower = [0.0, 0.0, 0.0] if lower is None else lower
+        upper = [float(global_rx), float(ry), float(rz)] if upper is None else upper
+        return cls(rx, ry, rz, rx if owned_x is None else int(owned_x), int(x_origin), global_rx,
+                   float(thresh), (ctypes.c_float * 3)(*[float(v) for v in lower]),
+                   (ctypes.c_float * 3)(*[float(v) for v in upper]))
+
+
+class P3DError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"prim3d_b200 status {status}: {message}")
+        self.status = status
+
+
+def lib():
+    """Load libprim3d_b200.so; there is no fallback if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built; run `python -m primitive3d_b200.build`")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
+        dp = ctypes.POINTER(McDesc)
+        L.p3d_abi_version.restype = ctypes.c_int
+        L.p3d_last_error.restype = ctypes.c_char_p
+        L.p3d_mc_workspace_bytes.restype = sz
+        L.p3d_mc_workspace_bytes.argtypes = [dp]
+        L.p3d_mc_count.restype = ctypes.c_int
+        L.p3d_mc_count.argtypes = [dp, vp, vp, sz, ctypes.POINTER(i64), vp]
+        L.p3d_mc_emit.restype = ctypes.c_int
+        L.p3d_mc_emit.argtypes = [dp, vp, vp, vp, vp, i64, vp]
+        L.p3d_mc_export_first_plane.restype = ctypes.c_int
+        L.p3d_mc_export_first_plane.argtypes = [dp, vp, vp, vp]
+        L.p3d_mc_import_halo_plane.restype = ctypes.c_int
+        L.p3d_mc_import_halo_plane.argtypes = [dp, vp, vp, i64, vp]
+        _bind_mt(L, vp, i64, sz)
+        _lib = L
+    return _lib
+
+
+def _bind_mt(L, vp, i64, sz):
+    pi64 = ctypes.POINTER(i64)
+    L.p3d_mt_codes_bytes.restype = sz
+    L.p3d_mt_codes_bytes.argtypes = [i64]
+    L.p3d_mt_classify.restype = ctypes.c_int
+    L.p3d_mt_classify.argtypes = [vp, i64, vp, i64, vp, vp, pi64, vp]
+    L.p3d_mt_workspace_bytes.restype = sz
+    L.p3d_mt_workspace_bytes.argtypes = [i64, i64, i64, i64]
+    L.p3d_mt_index.restype = ctypes.c_int
+    L.p3d_mt_index.argtypes = [vp, i64, i64, vp, vp, i64, i64, i64, vp, sz, pi64, vp]
+    L.p3d_mt_emit.restype = ctypes.c_int
+    L.p3d_mt_emit.argtypes = [vp, vp, i64, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp]
+    L.p3d_mt_backward.restype = ctypes.c_int
+    L.p3d_mt_backward.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+
+
+def abi_version():
+    return lib().p3d_abi_version()
+
+
+def check(status):
+    if status != P3D_OK:
+        raise P3DError(status, lib().p3d_last_error().decode())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _grid_ok(grid):
+    if not (grid.is_cuda and grid.is_contiguous() and grid.dtype == torch.float32 and grid.dim() == 3):
+        raise ValueError("grid must be a contiguous float32 CUDA tensor [Rx,Ry,Rz]")
+
+
+def mc_workspace_bytes(desc):
+    n = lib().p3d_mc_workspace_bytes(ctypes.byref(desc))
+    if n == 0:
+        raise P3DError(P3D_ERR_INVALID, "invalid descriptor")
+    return n
+
+
+def mc_count(desc, grid, workspace=None):
+    """-> (V, F, workspace).  Synchronises the current stream."""
+    _grid_ok(grid)
+    nbytes = mc_workspace_bytes(desc)
+    if workspace is None:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
+    counts = (ctypes.c_int64 * 2)()
+    with torch.cuda.device(grid.device):
+        check(lib().p3d_mc_count(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                 counts, _stream()))
+    return counts[0], counts[1], workspace
+
+
+def mc_emit(desc, grid, workspace, V, F, vertex_id_base=0):
+    """-> (vertices float32 [V,3], faces int32 [F,3]) on grid.device (asynchronous)."""
+    verts = torch.empty((V, 3), dtype=torch.float32, device=grid.device)
+    faces = torch.empty((F, 3), dtype=torch.int32, device=grid.device)
+    with torch.cuda.device(grid.device):
+        check(lib().p3d_mc_emit(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), verts.data_ptr(),
+                                faces.data_ptr(), int(vertex_id_base), _stream()))
+    return verts, faces
+
+
+def marching_cubes(grid, thresh, lower=None, upper=None):
+    """Single-GPU extraction through the C ABI (same outputs as prim3d.libPrim3D.marching_cubes)."""
+    desc = McDesc.make(grid.shape, thresh, lower, upper)
+    V, F, ws = mc_count(desc, grid)
+    return mc_emit(desc, grid, ws, V, F)
+
+
+def marching_tetrahedra(points, tets, sdf):
+    """Marching tetrahedra through the C ABI: points f32 [P,3], tets i64 [T,4] (mutated in place),
+    sdf f32 [P], all contiguous CUDA tensors -> (verts f32 [V,3], faces i64 [F,3], tet_idx i64 [F],
+    edges i64 [V,2])."""
+    if not (points.is_cuda and tets.is_cuda and sdf.is_cuda and points.is_contiguous() and tets.is_contiguous()
+            and sdf.is_contiguous() and points.dtype == torch.float32 and tets.dtype == torch.int64
+            and sdf.dtype == torch.float32):
+        raise ValueError("points/sdf must be contiguous float32 and tets contiguous int64 CUDA tensors")
+    L, dev = lib(), points.device
+    P, T = points.shape[0], tets.shape[0]
+    with torch.cuda.device(dev):
+        codes = torch.empty(L.p3d_mt_codes_bytes(T), dtype=torch.uint8, device=dev)
+        c = (ctypes.c_int64 * 3)()
+        check(L.p3d_mt_classify(points.data_ptr(), P, tets.data_ptr(), T, sdf.data_ptr(), codes.data_ptr(), c, _stream()))
+        n1, n2, ne = c[0], c[1], c[2]
+        ws = torch.empty(L.p3d_mt_workspace_bytes(T, n1, n2, ne), dtype=torch.uint8, device=dev)
+        v = (ctypes.c_int64 * 1)()
+        check(L.p3d_mt_index(tets.data_ptr(), T, P, sdf.data_ptr(), codes.data_ptr(), n1, n2, ne, ws.data_ptr(),
+                             ws.numel(), v, _stream()))
+        V, F = v[0], n1 + 2 * n2
+        verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        edges = torch.empty((V, 2), dtype=torch.int64, device=dev)
+        faces = torch.empty((F, 3), dtype=torch.int64, device=dev)
+        tet_idx = torch.empty((F,), dtype=torch.int64, device=dev)
+        check(L.p3d_mt_emit(points.data_ptr(), tets.data_ptr(), T, sdf.data_ptr(), codes.data_ptr(), n1, n2, ne, V,
+                            ws.data_ptr(), verts.data_ptr(), edges.data_ptr(), faces.data_ptr(), tet_idx.data_ptr(),
+                            _stream()))
+    return verts, faces, tet_idx, edges

@@ -1,0 +1,150 @@
+// primitive3d_b200/csrc/bindings.cpp -- the reference-facing module `prim3d.libPrim3D`.
+//
+// Mirrors the export list of /root/reference/src/pybind/bindings.cpp:13-32 (enable_optix, test,
+// RayCaster, create_raycaster, marching_cubes, save_mesh_as_ply) so `import prim3d` and the
+// reference's examples work unchanged.  It is a thin layer: argument checks with the reference's
+// error texts (Core/common.h:63-68), ATen allocation of outputs on the input's device, the
+// current CUDA stream and device guard, and calls into the torch-free C ABI
+// (include/prim3d_b200.h).  The only torch-header translation unit in the repo.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cstdio>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/prim3d_b200.h"
+
+namespace {
+
+using torch::Tensor;
+
+#define P3D_CHECK_CUDA(x) TORCH_CHECK(x.is_cuda(), #x " must be a CUDA tensor")
+#define P3D_CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")
+
+void check_status(p3d_status st, const char *what) {
+    TORCH_CHECK(st == P3D_OK, what, " failed (status ", static_cast<int>(st), "): ", p3d_last_error());
+}
+
+// prim3d::marching_cubes, marching_cubes.cu:212-305: same signature, same outputs
+// ([vertices float32 [V,3], faces int32 [F,3]] on the input's device).
+std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thresh, const std::vector<float> lower,
+                                   const std::vector<float> upper) {
+    P3D_CHECK_CUDA(density_grid);
+    P3D_CHECK_CONTIGUOUS(density_grid);
+    TORCH_CHECK(density_grid.ndimension() == 3);
+    TORCH_CHECK(density_grid.scalar_type() == torch::kFloat, "expected scalar type Float but found ",
+                density_grid.scalar_type());
+    TORCH_CHECK(lower.size() == 3 && upper.size() == 3, "lower and upper must have 3 elements");
+
+    const c10::cuda::CUDAGuard guard(density_grid.device());
+    cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+
+    p3d_mc_desc desc;
+    desc.rx = density_grid.size(0);
+    desc.ry = density_grid.size(1);
+    desc.rz = density_grid.size(2);
+    desc.owned_x = desc.rx;
+    desc.x_origin = 0;
+    desc.global_rx = desc.rx;
+    desc.thresh = thresh;
+    for (int i = 0; i < 3; ++i) {
+        desc.lower[i] = lower[i];
+        desc.upper[i] = upper[i];
+    }
+
+    const auto bytes_opt = torch::TensorOptions().dtype(torch::kUInt8).device(density_grid.device());
+    const size_t ws_bytes = p3d_mc_workspace_bytes(&desc);
+    TORCH_CHECK(ws_bytes > 0, "marching_cubes: invalid grid shape");
+    Tensor workspace = torch::empty({static_cast<int64_t>(ws_bytes)}, bytes_opt);
+
+    int64_t counts[2] = {0, 0};
+    check_status(p3d_mc_count(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), ws_bytes, counts, stream),
+                 "p3d_mc_count");
+
+    Tensor vertices = torch::empty({counts[0], 3}, density_grid.options());
+    Tensor faces = torch::empty({counts[1], 3}, density_grid.options().dtype(torch::kInt));
+    check_status(p3d_mc_emit(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), vertices.data_ptr<float>(),
+                             faces.data_ptr<int32_t>(), 0, stream),
+                 "p3d_mc_emit");
+    // `workspace` is released to the caching allocator here; the allocator keeps it alive for the
+    // kernels already queued on this stream.
+    return {vertices, faces};
+}
+
+// prim3d::save_mesh_as_ply, marching_cubes.cu:307-352: same binary-little-endian PLY bytes
+// (header text, 15-byte vertex records x,y,z,r,g,b, faces as int32 [3,a,b,c]), assembled in one
+// buffer and written with a single call instead of one ofstream.write per vertex.
+void save_mesh_as_ply(const std::string filename, Tensor vertices, Tensor faces, Tensor colors) {
+    P3D_CHECK_CONTIGUOUS(vertices);
+    P3D_CHECK_CONTIGUOUS(faces);
+    P3D_CHECK_CONTIGUOUS(colors);
+    vertices = vertices.to(torch::kCPU);
+    faces = faces.to(torch::kCPU);
+    colors = colors.to(torch::kCPU);
+    TORCH_CHECK(vertices.scalar_type() == torch::kFloat, "vertices must be float32");
+    TORCH_CHECK(faces.scalar_type() == torch::kInt, "faces must be int32");
+    TORCH_CHECK(colors.scalar_type() == torch::kByte, "colors must be uint8");
+
+    const int64_t nv = vertices.size(0), nf = faces.size(0);
+    std::string buf = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(nv) +
+                      "\nproperty float x\nproperty float y\nproperty float z\n"
+                      "property uchar red\nproperty uchar green\nproperty uchar blue\n"
+                      "element face " + std::to_string(nf) +
+                      "\nproperty list int int vertex_index\nend_header\n";
+    const size_t head = buf.size();
+    buf.resize(head + static_cast<size_t>(nv) * 15 + static_cast<size_t>(nf) * 16);
+    char *out = &buf[head];
+    const float *v = vertices.data_ptr<float>();
+    const uint8_t *c = colors.data_ptr<uint8_t>();
+    for (int64_t i = 0; i < nv; ++i, out += 15) {
+        std::memcpy(out, v + 3 * i, 12);
+        std::memcpy(out + 12, c + 3 * i, 3);
+    }
+    const int32_t *f = faces.data_ptr<int32_t>();
+    const int32_t three = 3;
+    for (int64_t i = 0; i < nf; ++i, out += 16) {
+        std::memcpy(out, &three, 4);
+        std::memcpy(out + 4, f + 3 * i, 12);
+    }
+    std::FILE *fp = std::fopen(filename.c_str(), "wb");
+    TORCH_CHECK(fp != nullptr, "cannot open ", filename);
+    const size_t written = std::fwrite(buf.data(), 1, buf.size(), fp);
+    std::fclose(fp);
+    TORCH_CHECK(written == buf.size(), "short write to ", filename);
+}
+
+// prim3d::test, Core/utils.cpp:10-12
+void test() { std::cout << "hello world!" << std::endl; }
+
+// Ray casting (ray_cast.h:55-74) is outside this repository's scope (SURVEY.md section 2, rows
+// 11-14); the names exist because prim3d/utility/ray_cast.py refers to them at import time.
+struct RayCaster {
+    std::vector<Tensor> invoke(const Tensor &, const Tensor &) {
+        TORCH_CHECK(false, "RayCaster is not part of the B200 marching-cubes/tetrahedra build");
+        return {};
+    }
+};
+
+RayCaster *create_raycaster(const Tensor &, const Tensor &) {
+    TORCH_CHECK(false, "create_raycaster is not part of the B200 marching-cubes/tetrahedra build");
+    return nullptr;
+}
+
+}  // namespace
+
+#include "bindings_mt.inc"
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "prim3d.libPrim3D -- B200-native marching cubes / marching tetrahedra behind the Primitive3D API";
+    m.attr("enable_optix") = false;
+    m.attr("abi_version") = p3d_abi_version();
+    m.def("test", &test);
+    py::class_<RayCaster>(m, "RayCaster").def("invoke", &RayCaster::invoke);
+    m.def("create_raycaster", &create_raycaster);
+    m.def("marching_cubes", &marching_cubes);
+    m.def("save_mesh_as_ply", &save_mesh_as_ply);
+    bind_marching_tetrahedra(m);
+}

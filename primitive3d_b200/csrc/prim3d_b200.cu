@@ -1,0 +1,203 @@
+// primitive3d_b200/csrc/prim3d_b200.cu -- host side of the C ABI declared in include/prim3d_b200.h.
+// Torch-free: plain CUDA runtime.  Replaces the orchestration of prim3d::marching_cubes,
+// /root/reference/src/prim3d/Utility/marching_cubes.cu:212-305.
+#include "../../include/prim3d_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "mc_kernels.cuh"
+#include "p3d_error.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+p3d_status fail(p3d_status st, const std::string &msg) { return p3d::set_error(st, msg); }
+
+#define P3D_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(P3D_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(e_));          \
+    } while (0)
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
+    if (!d || d->rx < 1 || d->ry < 1 || d->rz < 1) return false;
+    if (d->owned_x < 0 || d->owned_x > d->rx || d->rx - d->owned_x > 1) return false;
+    if (d->rz > (int64_t)INT_MAX - 64 || d->rx * d->ry > (int64_t)1 << 40) return false;
+    g->rx = d->rx;
+    g->ry = d->ry;
+    g->rz = d->rz;
+    g->owned_x = d->owned_x;
+    g->wz = (int32_t)((d->rz + 31) / 32);
+    g->pieces = (g->wz + p3d::kPieceWords - 1) / p3d::kPieceWords;
+    g->owned_rows = d->owned_x * d->ry;
+    g->num_tiles = (g->owned_rows + p3d::kRowsPerTile - 1) / p3d::kRowsPerTile;
+    return true;
+}
+
+struct Layout {
+    size_t header, bits, rowv, rowf, status_v, status_f, total;
+};
+
+Layout make_layout(const p3d::McGeom &g) {
+    Layout l;
+    const size_t rows = (size_t)(g.rx * g.ry);
+    size_t off = 0;
+    l.header = off;   off += align_up(sizeof(p3d::McHeader));
+    l.status_v = off; off += align_up((size_t)g.num_tiles * 8);
+    l.status_f = off; off += align_up((size_t)g.num_tiles * 8);
+    l.rowv = off;     off += align_up(rows * sizeof(uint4));
+    l.rowf = off;     off += align_up(rows * 8);
+    l.bits = off;     off += align_up(rows * (size_t)g.wz * 4);
+    l.total = off;
+    return l;
+}
+
+p3d::McWorkspace bind(void *base, const Layout &l) {
+    char *b = static_cast<char *>(base);
+    p3d::McWorkspace ws;
+    ws.header = reinterpret_cast<p3d::McHeader *>(b + l.header);
+    ws.status_v = reinterpret_cast<unsigned long long *>(b + l.status_v);
+    ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
+    ws.rowv = reinterpret_cast<uint4 *>(b + l.rowv);
+    ws.rowf = reinterpret_cast<unsigned long long *>(b + l.rowf);
+    ws.bits = reinterpret_cast<uint32_t *>(b + l.bits);
+    return ws;
+}
+
+// One pinned 16-byte landing pad per host thread for the {V,F} readback.
+int64_t *pinned_counts() {
+    thread_local int64_t *buf = nullptr;
+    if (!buf && cudaHostAlloc(reinterpret_cast<void **>(&buf), 4 * sizeof(int64_t), cudaHostAllocPortable) != cudaSuccess)
+        buf = nullptr;
+    return buf;
+}
+
+}  // namespace
+
+namespace p3d {
+p3d_status set_error(p3d_status st, const std::string &msg) {
+    g_last_error = msg;
+    return st;
+}
+}  // namespace p3d
+
+extern "C" {
+
+int p3d_abi_version(void) { return P3D_ABI_VERSION; }
+
+const char *p3d_last_error(void) { return g_last_error.c_str(); }
+
+size_t p3d_mc_workspace_bytes(const p3d_mc_desc *desc) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return 0;
+    return make_layout(g).total;
+}
+
+p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace, size_t workspace_bytes,
+                        int64_t *counts_host, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_count: invalid descriptor");
+    if (!grid || !workspace || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_count: null pointer");
+    const Layout l = make_layout(g);
+    if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_count: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_count: workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const p3d::McWorkspace ws = bind(workspace, l);
+
+    // header + both look-back status arrays are contiguous: one memset
+    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.rowv, s));
+    p3d::launch_classify(grid, g, desc->thresh, ws.bits, s);
+    p3d::launch_count_scan(g, ws, s);
+    P3D_CUDA(cudaGetLastError());
+
+    int64_t *pin = pinned_counts();
+    int64_t *dst = pin ? pin : counts_host;
+    P3D_CUDA(cudaMemcpyAsync(dst, &ws.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaStreamSynchronize(s));
+    counts_host[0] = dst[0];
+    counts_host[1] = dst[1];
+    if (counts_host[0] > INT32_MAX)
+        return fail(P3D_ERR_OVERFLOW, "p3d_mc_count: vertex count exceeds the int32 face-index contract");
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *workspace, float *vertices,
+                       int32_t *faces, int64_t vertex_id_base, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_emit: invalid descriptor");
+    if (!grid || !workspace) return fail(P3D_ERR_INVALID, "p3d_mc_emit: null pointer");
+    if (vertex_id_base < 0 || vertex_id_base > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_emit: vertex_id_base out of int32 range");
+    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_emit: global_rx must be >= 1");
+    const Layout l = make_layout(g);
+    const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
+
+    p3d::McEmitParams prm;
+    prm.thresh = desc->thresh;
+    // marching_cubes.cu:290-297 -- offset = lower; scale = (upper - lower) / resolution, where the
+    // reference's y term reads upper[2] (not upper[1]); replicated because it is observable.
+    prm.scale[0] = (desc->upper[0] - desc->lower[0]) / static_cast<float>(desc->global_rx);
+    prm.scale[1] = (desc->upper[2] - desc->lower[1]) / static_cast<float>(desc->ry);
+    prm.scale[2] = (desc->upper[2] - desc->lower[2]) / static_cast<float>(desc->rz);
+    prm.offset[0] = desc->lower[0];
+    prm.offset[1] = desc->lower[1];
+    prm.offset[2] = desc->lower[2];
+    prm.x_origin = desc->x_origin;
+    prm.vertex_id_base = static_cast<int32_t>(vertex_id_base);
+    p3d::launch_emit(grid, g, ws, prm, vertices, faces, static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *workspace, uint32_t *table_out, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !workspace || !table_out) return fail(P3D_ERR_INVALID, "p3d_mc_export_first_plane: invalid argument");
+    const Layout l = make_layout(g);
+    const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
+    P3D_CUDA(cudaMemcpyAsync(table_out, ws.rowv, (size_t)g.ry * sizeof(uint4), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace, const uint32_t *table_in, int64_t delta,
+                                    void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !workspace || !table_in) return fail(P3D_ERR_INVALID, "p3d_mc_import_halo_plane: invalid argument");
+    if (g.rx != g.owned_x + 1) return fail(P3D_ERR_INVALID, "p3d_mc_import_halo_plane: descriptor has no halo plane");
+    if (delta < 0 || delta > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_import_halo_plane: delta out of range");
+    const Layout l = make_layout(g);
+    const p3d::McWorkspace ws = bind(workspace, l);
+    p3d::launch_import_halo(ws.rowv + g.owned_rows, table_in, g.ry, static_cast<uint32_t>(delta),
+                            static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn alloc, void *alloc_ctx, float **vertices,
+                      int32_t **faces, int64_t *num_vertices, int64_t *num_faces, void *stream) {
+    if (!alloc || !vertices || !faces || !num_vertices || !num_faces) return fail(P3D_ERR_INVALID, "p3d_mc_run: null pointer");
+    const size_t bytes = p3d_mc_workspace_bytes(desc);
+    if (!bytes) return fail(P3D_ERR_INVALID, "p3d_mc_run: invalid descriptor");
+    void *ws = alloc(alloc_ctx, bytes);
+    if (!ws) return fail(P3D_ERR_CUDA, "p3d_mc_run: workspace allocation failed");
+    int64_t counts[2] = {0, 0};
+    p3d_status st = p3d_mc_count(desc, grid, ws, bytes, counts, stream);
+    if (st != P3D_OK) return st;
+    *num_vertices = counts[0];
+    *num_faces = counts[1];
+    *vertices = static_cast<float *>(alloc(alloc_ctx, (size_t)(counts[0] > 0 ? counts[0] : 1) * 12));
+    *faces = static_cast<int32_t *>(alloc(alloc_ctx, (size_t)(counts[1] > 0 ? counts[1] : 1) * 12));
+    if (!*vertices || !*faces) return fail(P3D_ERR_CUDA, "p3d_mc_run: output allocation failed");
+    return p3d_mc_emit(desc, grid, ws, *vertices, *faces, 0, stream);
+}
+
+}  // extern "C"

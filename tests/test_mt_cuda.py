@@ -1,0 +1,129 @@
+"""GPU parity tests of the marching-tetrahedra path against (a) outputs of the REAL reference
+stored in tests/golden (made by tests/golden/make_golden.py), (b) the numpy oracle on larger
+seeded inputs, (c) the real reference module run on the same GPU when it has been staged in
+oracle/_ref.  Bar: bit-exact verts (fp32), identical int64 faces / tet_idx, identical in-place
+orientation fix of `tets`."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs, mt
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = ["kat", "fixture", "random0", "random1", "kuhn8", "kuhn8_noise"]
+
+
+def run_capi(pts, tets, sdf):
+    from primitive3d_b200 import capi
+    t = torch.from_numpy(tets.copy()).cuda()
+    v, f, ti, e = capi.marching_tetrahedra(torch.from_numpy(pts).cuda(), t, torch.from_numpy(sdf).cuda())
+    torch.cuda.synchronize()
+    return v.cpu().numpy(), f.cpu().numpy(), ti.cpu().numpy(), e.cpu().numpy(), t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_capi_matches_reference_golden(name):
+    g = np.load(os.path.join(HERE, "golden", f"mt_{name}.npz"))
+    v, f, ti, e, tets_after = run_capi(g["points"], g["tets"], g["sdf"])
+    assert np.array_equal(tets_after, g["tets_after"])
+    assert v.shape == g["verts"].shape and f.shape == g["faces"].shape
+    assert np.array_equal(v.view(np.uint32), g["verts"].view(np.uint32))
+    assert np.array_equal(f, g["faces"]) and np.array_equal(ti, g["tet_idx"])
+    assert (e[:, 0] < e[:, 1]).all()
+
+
+@pytest.mark.parametrize("n", [32, 64])
+def test_kuhn_grid_matches_oracle(n):
+    pts, tets, sdf = inputs.kuhn_tet_grid(n)
+    v, f, ti, e, tets_after = run_capi(pts, tets, sdf)
+    o_tets = tets.copy()
+    ov, of, oti = mt.marching_tetrahedras(pts, o_tets, sdf, True)
+    if n == 32:
+        assert (len(ov), len(of)) == (3314, 6624)
+    assert np.array_equal(tets_after, o_tets)
+    assert np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+    assert np.array_equal(f, of) and np.array_equal(ti, oti)
+
+
+def test_noisy_sdf_many_valid_tets():
+    pts, tets, _ = inputs.kuhn_tet_grid(24)
+    sdf = np.random.default_rng(5).uniform(-1, 1, len(pts)).astype(np.float32)
+    sdf[::17] = 0.0
+    v, f, ti, e, tets_after = run_capi(pts, tets, sdf)
+    o_tets = tets.copy()
+    ov, of, oti = mt.marching_tetrahedras(pts, o_tets, sdf, True)
+    assert np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+    assert np.array_equal(f, of) and np.array_equal(ti, oti) and np.array_equal(tets_after, o_tets)
+
+
+def test_python_entry_point_contract():
+    """prim3d.marching_tetrahedras: CUDA and CPU tensors, in-place mutation, return_tet_idx,
+    empty result (reference marching_tetrahedras.py:89-94,148,225-235)."""
+    import prim3d
+    g = np.load(os.path.join(HERE, "golden", "mt_fixture.npz"))
+    for dev in ("cuda", "cpu"):
+        pts = torch.from_numpy(g["points"]).to(dev)
+        sdf = torch.from_numpy(g["sdf"]).to(dev)
+        tets = torch.from_numpy(g["tets"].copy()).to(dev)
+        v, f, ti = prim3d.marching_tetrahedras(pts, tets, sdf, return_tet_idx=True)
+        assert v.device.type == dev and f.device.type == dev and f.dtype == torch.int64
+        assert np.array_equal(tets.cpu().numpy(), g["tets_after"])           # caller's tensor mutated
+        assert np.array_equal(v.cpu().numpy().view(np.uint32), g["verts"].view(np.uint32))
+        assert np.array_equal(f.cpu().numpy(), g["faces"]) and np.array_equal(ti.cpu().numpy(), g["tet_idx"])
+        out = prim3d.marching_tetrahedras(pts, tets, sdf)
+        assert len(out) == 2
+    pts = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=torch.float32).cuda()
+    v, f, ti = prim3d.marching_tetrahedras(pts, torch.tensor([[0, 1, 2, 3]]).cuda(), torch.ones(4).cuda(), True)
+    assert v.shape == (0, 3) and f.shape == (0, 3) and ti.shape == (0,)
+
+
+def test_gradients_match_torch_autograd_of_the_reference_formula():
+    """The reference's verts are differentiable w.r.t. vertices and sdf
+    (marching_tetrahedras.py:175-189); compare our backward with autograd on that formula."""
+    import prim3d
+    g = np.load(os.path.join(HERE, "golden", "mt_kuhn8_noise.npz"))
+    pts = torch.from_numpy(g["points"]).cuda().requires_grad_(True)
+    sdf = torch.from_numpy(g["sdf"]).cuda().requires_grad_(True)
+    tets = torch.from_numpy(g["tets"].copy()).cuda()
+    v, f = prim3d.marching_tetrahedras(pts, tets, sdf)
+    w = torch.randn_like(v)
+    (v * w).sum().backward()
+    gp, gs = pts.grad.clone(), sdf.grad.clone()
+    # reference formula with autograd, on the same unique crossing edges
+    p2 = torch.from_numpy(g["points"]).cuda().requires_grad_(True)
+    s2 = torch.from_numpy(g["sdf"]).cuda().requires_grad_(True)
+    from primitive3d_b200 import capi
+    e = capi.marching_tetrahedra(p2.detach(), tets.clone(), s2.detach())[3]
+    ev, es = p2[e], s2[e].clone()
+    es = torch.stack([es[:, 0], -es[:, 1]], 1)
+    wts = torch.flip(es, [1]) / es.sum(1, keepdim=True)
+    v2 = (ev * wts[..., None]).sum(1)
+    assert torch.equal(v2.detach(), v.detach())
+    (v2 * w).sum().backward()
+    assert torch.allclose(gp, p2.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(gs, s2.grad, rtol=1e-3, atol=1e-3 * float(s2.grad.abs().max()))
+
+
+def test_against_reference_module_on_gpu():
+    """The reference's own torch implementation run on the same GPU (staged copy in oracle/_ref)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_marching_tetrahedras.py")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/ref_marching_tetrahedras.py not staged")
+    spec = importlib.util.spec_from_file_location("ref_mt", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    pts, tets, sdf = inputs.kuhn_tet_grid(48)
+    margin = mt.orientation_margin(pts, tets)
+    assert margin.min() > 1e-6   # no numerically degenerate tets, torch.det's sign is reliable
+    P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sdf).cuda()
+    t_ref = torch.from_numpy(tets.copy()).cuda()
+    rv, rf, rti = ref.marching_tetrahedras(P, t_ref, S, True)
+    v, f, ti, e, tets_after = run_capi(pts, tets, sdf)
+    assert np.array_equal(tets_after, t_ref.cpu().numpy())
+    assert np.array_equal(v.view(np.uint32), rv.cpu().numpy().view(np.uint32))
+    assert np.array_equal(f, rf.cpu().numpy()) and np.array_equal(ti, rti.cpu().numpy())
