@@ -92,6 +92,12 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
 p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *workspace,
                        float *vertices, int32_t *faces, int64_t vertex_id_base, void *stream);
 
+/* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
+ * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: classify, 2: count+scan.
+ * The emit stage is p3d_mc_emit itself. */
+p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage,
+                              void *stream);
+
 /* Multi-GPU halo exchange of vertex numbering (16 bytes per row of one plane):
  * export copies the row table of local plane 0 into table_out (uint32[4*ry], device);
  * import installs the next shard's exported table as the numbering of this shard's halo

@@ -18,6 +18,10 @@ def lib():
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             raise ImportError(f"{_LIB_PATH} is missing; run `make -C oracle` (or __graft_entry__.build())")
+        # libgomp reads these once, when it is first loaded; without a binding policy the sandbox
+        # kernels used here were seen to stack every OpenMP thread on one core (no speed-up at all)
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "cores")
         _lib = ctypes.CDLL(_LIB_PATH)
         i64, f32, vp = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
         _lib.p3d_oracle_mc_count.restype = ctypes.c_int

@@ -134,14 +134,14 @@ int p3d_oracle_mc_count(const float *grid, int64_t rx, int64_t ry, int64_t rz, f
  * `base`; ids[(y*Rz+z)*3+axis] = id or -1.  When verts != NULL also writes the
  * interpolated positions (gen_vertices_kernel, marching_cubes.cu:70-138) followed
  * by the bounding-box transform (:290-298). */
-static void plane_vertices(const grid_t *g, int64_t x, int64_t base, int64_t *ids, float *verts,
+static void plane_vertices(const grid_t *g, int64_t x, int64_t base, int32_t *ids, float *verts,
                            const float scale[3], const float offset[3]) {
     int64_t next = base;
     for (int64_t y = 0; y < g->ry; ++y)
         for (int64_t z = 0; z < g->rz; ++z) {
             const float self = at(g, x, y, z);
             const int inside = self > g->thresh;
-            int64_t *slot = ids + (y * g->rz + z) * 3;
+            int32_t *slot = ids + (y * g->rz + z) * 3;
             for (int axis = 0; axis < 3; ++axis) {
                 slot[axis] = -1;
                 const int64_t p = axis == 0 ? x : (axis == 1 ? y : z);
@@ -149,7 +149,7 @@ static void plane_vertices(const grid_t *g, int64_t x, int64_t base, int64_t *id
                 if (p >= r - 1) continue;
                 const float nb = at(g, x + (axis == 0), y + (axis == 1), z + (axis == 2));
                 if (inside == (nb > g->thresh)) continue;
-                slot[axis] = next;
+                slot[axis] = (int32_t)next;
                 if (verts) {
                     const float dt = (g->thresh - self) / (nb - self);
                     float pos[3] = {(float)x, (float)y, (float)z};
@@ -166,7 +166,7 @@ static void plane_vertices(const grid_t *g, int64_t x, int64_t base, int64_t *id
 
 /* Faces of the cells of plane x (gen_faces_kernel, marching_cubes.cu:140-209).
  * ids0 / ids1 are the vertex-id planes of x and x+1. */
-static void plane_faces(const grid_t *g, int64_t x, const int64_t *ids0, const int64_t *ids1,
+static void plane_faces(const grid_t *g, int64_t x, const int32_t *ids0, const int32_t *ids1,
                         int32_t *faces, int64_t tri_base, int *missing) {
     int64_t t = tri_base;
     const int64_t rz = g->rz;
@@ -175,15 +175,15 @@ static void plane_faces(const grid_t *g, int64_t x, const int64_t *ids0, const i
             const int m = cube_case(g, x, y, z);
             if (g_ntri[m] == 0) continue;
 #define ID(plane, yy, zz, ax) (plane)[((yy)*rz + (zz)) * 3 + (ax)]
-            const int64_t e[12] = {
+            const int32_t e[12] = {
                 ID(ids0, y, z, 0),     ID(ids1, y, z, 1),         ID(ids0, y + 1, z, 0),     ID(ids0, y, z, 1),
                 ID(ids0, y, z + 1, 0), ID(ids1, y, z + 1, 1),     ID(ids0, y + 1, z + 1, 0), ID(ids0, y, z + 1, 1),
                 ID(ids0, y, z, 2),     ID(ids1, y, z, 2),         ID(ids1, y + 1, z, 2),     ID(ids0, y + 1, z, 2)};
 #undef ID
             for (int i = 0; i < 3 * g_ntri[m]; ++i) {
-                const int64_t id = e[g_table[m][i]];
+                const int32_t id = e[g_table[m][i]];
                 if (id < 0) *missing = 1; /* the reference printf()s here, :204-206 */
-                faces[t * 3 + i] = (int32_t)id;
+                faces[t * 3 + i] = id;
             }
             t += g_ntri[m];
         }
@@ -225,18 +225,27 @@ int p3d_oracle_mc_extract(const float *grid, int64_t rx, int64_t ry, int64_t rz,
     int missing = 0;
 #pragma omp parallel reduction(| : missing)
     {
+        /* each thread walks a contiguous block of planes with two rolling id planes, so the
+         * ids of plane x+1 computed for the cells of plane x are reused as plane x+1's own */
+        int nt = 1, tid = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        tid = omp_get_thread_num();
+#endif
+        const int64_t xa = rx * tid / nt, xb = rx * (tid + 1) / nt;
         const size_t plane = (size_t)ry * (size_t)rz * 3;
-        int64_t *ids0 = (int64_t *)malloc(plane * sizeof(int64_t));
-        int64_t *ids1 = (int64_t *)malloc(plane * sizeof(int64_t));
-#pragma omp for schedule(static)
-        for (int64_t x = 0; x < rx; ++x) {
-            plane_vertices(&g, x, vbase[x], ids0, verts, scale, offset);
+        int32_t *ids0 = (int32_t *)malloc(plane * sizeof(int32_t));
+        int32_t *ids1 = (int32_t *)malloc(plane * sizeof(int32_t));
+        for (int64_t x = xa; x < xb; ++x) {
+            if (x == xa) plane_vertices(&g, x, vbase[x], ids0, verts, scale, offset);
             if (x + 1 < rx) {
-                /* ids of the next plane are needed by this plane's cells; positions are
-                 * written by the iteration that owns that plane */
-                plane_vertices(&g, x + 1, vbase[x + 1], ids1, NULL, scale, offset);
+                /* positions of plane x+1 are written here only if this thread owns that plane */
+                plane_vertices(&g, x + 1, vbase[x + 1], ids1, x + 1 < xb ? verts : NULL, scale, offset);
                 plane_faces(&g, x, ids0, ids1, faces, tbase[x], &missing);
             }
+            int32_t *t = ids0;
+            ids0 = ids1;
+            ids1 = t;
         }
         free(ids0);
         free(ids1);

@@ -55,6 +55,8 @@ def lib():
         L.p3d_mc_count.argtypes = [dp, vp, vp, sz, ctypes.POINTER(i64), vp]
         L.p3d_mc_emit.restype = ctypes.c_int
         L.p3d_mc_emit.argtypes = [dp, vp, vp, vp, vp, i64, vp]
+        L.p3d_mc_debug_stage.restype = ctypes.c_int
+        L.p3d_mc_debug_stage.argtypes = [dp, vp, vp, ctypes.c_int, vp]
         L.p3d_mc_export_first_plane.restype = ctypes.c_int
         L.p3d_mc_export_first_plane.argtypes = [dp, vp, vp, vp]
         L.p3d_mc_import_halo_plane.restype = ctypes.c_int

@@ -153,7 +153,24 @@ p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *w
     prm.offset[2] = desc->lower[2];
     prm.x_origin = desc->x_origin;
     prm.vertex_id_base = static_cast<int32_t>(vertex_id_base);
+    P3D_CUDA(cudaMemsetAsync(&ws.header->ticket_emit, 0, sizeof(unsigned int), static_cast<cudaStream_t>(stream)));
     p3d::launch_emit(grid, g, ws, prm, vertices, faces, static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !grid || !workspace) return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: invalid argument");
+    const Layout l = make_layout(g);
+    const p3d::McWorkspace ws = bind(workspace, l);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (stage) {
+        case 0: P3D_CUDA(cudaMemsetAsync(workspace, 0, l.rowv, s)); break;
+        case 1: p3d::launch_classify(grid, g, desc->thresh, ws.bits, s); break;
+        case 2: p3d::launch_count_scan(g, ws, s); break;
+        default: return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: stage must be 0, 1 or 2");
+    }
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }

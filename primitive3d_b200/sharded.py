@@ -1,0 +1,104 @@
+"""Multi-GPU marching cubes: dim-0 slab decomposition, one process per GPU.
+
+The reference is single-GPU; this is the sharding the path
+admits naturally:
+
+  * tensor dim 0 (the slowest axis of idx = i*(Ry*Rz) + j*Rz + k, marching_cubes.cu:20) is split
+    into `world` contiguous plane ranges; rank r holds its planes plus ONE halo plane (the first
+    plane of rank r+1), because the cells and +x edges of its last plane read it;
+  * every rank runs the same three kernels on its slab (no data-path collective);
+  * the only exchange is tiny: an all-gather of {V_r, F_r} (16 bytes per rank) whose exclusive
+    prefix gives each rank the global id of its first vertex / face, and an all-gather of each
+    rank's first-plane row table (16 bytes per row of one plane) so the cells next to a slab
+    boundary can name the vertices the next rank owns;
+  * outputs stay sharded: rank r returns its vertices and its faces, the faces holding GLOBAL
+    vertex ids.  Concatenating the shards in rank order gives exactly the single-GPU result.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+def slab_range(global_rx, world, rank):
+    """Planes [x0, x1) owned by `rank`: contiguous, sizes differ by at most one."""
+    base, rem = divmod(int(global_rx), int(world))
+    x0 = rank * base + min(rank, rem)
+    return x0, x0 + base + (1 if rank < rem else 0)
+
+
+def slab_with_halo(global_rx, world, rank):
+    """Planes [x0, x1_halo) a rank must hold in memory: its own plus one halo plane (none for the last)."""
+    x0, x1 = slab_range(global_rx, world, rank)
+    return x0, min(x1 + 1, int(global_rx))
+
+
+def exclusive_offsets(counts, rank):
+    """counts: sequence of (V_r, F_r) per rank -> (v_offset, f_offset, V_total, F_total) for `rank`."""
+    v_off = sum(int(c[0]) for c in counts[:rank])
+    f_off = sum(int(c[1]) for c in counts[:rank])
+    return v_off, f_off, sum(int(c[0]) for c in counts), sum(int(c[1]) for c in counts)
+
+
+def gather_counts(V, F, device, group=None):
+    """All-gather of the per-rank {V, F} (int64 x 2).  Works on NCCL (CUDA tensors) and gloo (CPU)."""
+    world = dist.get_world_size(group)
+    mine = torch.tensor([int(V), int(F)], dtype=torch.int64, device=device)
+    out = torch.empty(world * 2, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return [tuple(r) for r in out.view(world, 2).cpu().tolist()]
+
+
+@dataclass
+class SlabMesh:
+    vertices: torch.Tensor      # float32 [V_r, 3], this rank's vertices
+    faces: torch.Tensor         # int32 [F_r, 3], GLOBAL vertex ids
+    v_offset: int               # global id of vertices[0]
+    f_offset: int               # global index of faces[0]
+    num_vertices_total: int
+    num_faces_total: int
+
+
+def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None, group=None):
+    """Extract this rank's shard.
+
+    slab: contiguous float32 CUDA tensor holding planes [x_begin, x_begin + slab.shape[0]) of the
+    global grid, i.e. the rank's own planes plus one halo plane unless it is the last rank.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    x0, x1 = slab_range(global_rx, world, rank)
+    if x0 != x_begin or slab.shape[0] != min(x1 + 1, global_rx) - x0:
+        raise ValueError(f"rank {rank}: slab must hold planes [{x0}, {min(x1 + 1, global_rx)})")
+    owned = x1 - x0
+    ry, rz = slab.shape[1], slab.shape[2]
+    lower = [0.0, 0.0, 0.0] if lower is None else lower
+    upper = [float(global_rx), float(ry), float(rz)] if upper is None else upper
+    desc = capi.McDesc.make(slab.shape, thresh, lower, upper, owned_x=owned, x_origin=x0, global_rx=global_rx)
+
+    V, F, ws = capi.mc_count(desc, slab)
+    if world == 1:
+        verts, faces = capi.mc_emit(desc, slab, ws, V, F, 0)
+        return SlabMesh(verts, faces, 0, 0, V, F)
+
+    L = capi.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    counts = gather_counts(V, F, slab.device, group)
+    v_off, f_off, v_tot, f_tot = exclusive_offsets(counts, rank)
+    if v_tot > 2 ** 31 - 1:
+        raise OverflowError("global vertex count exceeds the int32 face-index contract")
+
+    # numbering of the boundary plane: everybody publishes its first-plane row table
+    table = torch.empty((ry, 4), dtype=torch.int32, device=slab.device)
+    capi.check(L.p3d_mc_export_first_plane(ctypes.byref(desc), ws.data_ptr(), table.data_ptr(), stream))
+    tables = torch.empty(world * ry * 4, dtype=torch.int32, device=slab.device)
+    dist.all_gather_into_tensor(tables, table.view(-1), group=group)
+    tables = tables.view(world, ry, 4)
+    if rank + 1 < world:
+        capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(desc), ws.data_ptr(), tables[rank + 1].data_ptr(), int(V),
+                                              stream))
+    verts, faces = capi.mc_emit(desc, slab, ws, V, F, v_off)
+    return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)
