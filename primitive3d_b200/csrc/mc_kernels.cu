@@ -114,17 +114,27 @@ void launch_classify(const float *grid, const McGeom &g, float thresh, uint32_t 
 struct RowPtrs {
     const uint32_t *a, *b, *c, *d;
     bool has_x, has_y;  // x+1 < rx, y+1 < ry
+    int64_t x, y;
 };
 
 __device__ __forceinline__ RowPtrs row_ptrs(const uint32_t *bits, const McGeom &g, int64_t row) {
     RowPtrs r;
-    const int64_t x = row / g.ry, y = row - x * g.ry;
+    int64_t x, y;
+    if (g.rx * g.ry <= 0x7fffffffll) {
+        x = (uint32_t)row / (uint32_t)g.ry;
+        y = (uint32_t)row - (uint32_t)x * (uint32_t)g.ry;
+    } else {
+        x = row / g.ry;
+        y = row - x * g.ry;
+    }
     r.has_x = x + 1 < g.rx;
     r.has_y = y + 1 < g.ry;
     r.a = bits + row * g.wz;
     r.b = r.a + (r.has_x ? g.ry * (int64_t)g.wz : 0);
     r.d = r.a + (r.has_y ? g.wz : 0);
     r.c = r.b + (r.has_y ? g.wz : 0);
+    r.x = x;
+    r.y = y;
     return r;
 }
 
@@ -165,101 +175,137 @@ __device__ __forceinline__ uint32_t active_cells(const Piece &p, uint32_t zv, bo
     return cells ? ((any & ~all) & zv) : 0u;
 }
 
-// 8-bit cube case of the cell at bit i (corner order of marching_cubes.cu:168-176).
-__device__ __forceinline__ uint32_t cube_case(uint32_t ra, uint32_t rb, uint32_t rc, uint32_t rd) {
-    // r* = two bits of a row: bit0 = sample z, bit1 = sample z+1
-    return (ra & 1u) | ((rb & 1u) << 1) | ((rc & 1u) << 2) | ((rd & 1u) << 3) | ((ra >> 1) << 4) | ((rb >> 1) << 5) |
-           ((rc >> 1) << 6) | ((rd >> 1) << 7);
+// 8-bit cube case of the cell at bit i (corner order of marching_cubes.cu:168-176) from the packed
+// words {a,b,c,d} and their one-sample-shifted copies
+__device__ __forceinline__ uint32_t cube_case_at(const uint4 &w, const uint4 &w2, int i) {
+    return ((w.x >> i) & 1u) | (((w.y >> i) & 1u) << 1) | (((w.z >> i) & 1u) << 2) | (((w.w >> i) & 1u) << 3) |
+           (((w2.x >> i) & 1u) << 4) | (((w2.y >> i) & 1u) << 5) | (((w2.z >> i) & 1u) << 6) | (((w2.w >> i) & 1u) << 7);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: per-row counts + single-pass decoupled look-back scan over CTA tiles.
-// Replaces count_vertices_faces_kernel (:4-68) and its two global atomic counters.
+// K2a: per-row counts from the bit words.  Replaces count_vertices_faces_kernel (:4-68) and its
+// two global atomic counters.  rowv[row] = {nx, ny, nz, nf} (turned into offsets by K2b).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowsPerTile * 32) k_count_scan(McGeom g, McWorkspace ws) {
+__global__ void __launch_bounds__(256) k_row_count(McGeom g, McWorkspace ws) {
     __shared__ uint8_t s_ntri[256];
-    __shared__ uint32_t s_cnt[kRowsPerTile][4];
-    __shared__ unsigned long long s_rowv[kRowsPerTile], s_rowf[kRowsPerTile];
-    __shared__ unsigned int s_tile;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = (uint8_t)(c_case_table[i] >> 60);
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < g.owned_rows; row += nwarps) {
+        const RowPtrs r = row_ptrs(ws.bits, g, row);
+        const bool cells = r.has_x && r.has_y;
+        uint32_t nx = 0, ny = 0, nz = 0, nf = 0;
+        for (int pc = 0; pc < g.pieces; ++pc) {
+            const int w = pc * kPieceWords + lane;
+            const Piece p = load_piece(r, w, g.wz, lane);
+            const uint32_t zv = zvalid_mask(w, g.rz);
+            if (r.has_x) nx += __popc(p.a ^ p.b);       // :29-33
+            if (r.has_y) ny += __popc(p.a ^ p.d);       // :35-39
+            nz += __popc((p.a ^ p.a2) & zv);            // :41-45
+            uint32_t act = active_cells(p, zv, cells);  // :48-66
+            const uint4 w4 = make_uint4(p.a, p.b, p.c, p.d), w42 = make_uint4(p.a2, p.b2, p.c2, p.d2);
+            while (act) {
+                const int i = __ffs(act) - 1;
+                act &= act - 1;
+                nf += s_ntri[cube_case_at(w4, w42, i)];
+            }
+        }
+        // one packed reduction: nx,ny,nz <= rz (< 2^31 / 32 per lane) ... keep them separate but cheap
+        const unsigned long long lo = warp_sum64(((unsigned long long)ny << 32) | nx);
+        const unsigned long long hi = warp_sum64(((unsigned long long)nf << 32) | nz);
+        if (lane == 0) ws.rowv[row] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+}
 
+// ---------------------------------------------------------------------------------------------
+// K2b: exclusive scan of the per-row counts -- single pass, decoupled look-back over tiles of
+// 2048 rows (no CUB / thrust).  rowv[row] becomes {vx, vy, vz, nf}: first vertex id of the row's
+// x-, y- and z-edge groups; rowf[row] = first face of the row.  Totals go to the header.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanRowsPerThread = 8;
+constexpr int kScanTile = 256 * kScanRowsPerThread;
+
+__global__ void __launch_bounds__(256) k_row_scan(McGeom g, McWorkspace ws, int64_t num_scan_tiles) {
+    __shared__ unsigned long long s_warp[2][8];
+    __shared__ unsigned long long s_excl[2];
+    __shared__ unsigned int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ws.header->ticket, 1u);
         __syncthreads();
         const int64_t tile = s_tile;
-        if (tile >= g.num_tiles) break;
-
-        const int64_t row = tile * kRowsPerTile + warp;
-        uint32_t nx = 0, ny = 0, nz = 0, nf = 0;
-        if (row < g.owned_rows) {
-            const RowPtrs r = row_ptrs(ws.bits, g, row);
-            const bool cells = r.has_x && r.has_y;
-            for (int pc = 0; pc < g.pieces; ++pc) {
-                const int w = pc * kPieceWords + lane;
-                const Piece p = load_piece(r, w, g.wz, lane);
-                const uint32_t zv = zvalid_mask(w, g.rz);
-                if (r.has_x) nx += __popc(p.a ^ p.b);       // :29-33
-                if (r.has_y) ny += __popc(p.a ^ p.d);       // :35-39
-                nz += __popc((p.a ^ p.a2) & zv);            // :41-45
-                uint32_t act = active_cells(p, zv, cells);  // :48-66
-                while (act) {
-                    const int i = __ffs(act) - 1;
-                    act &= act - 1;
-                    nf += s_ntri[cube_case((p.a >> i) & 1u | (((p.a2 >> i) & 1u) << 1),
-                                           (p.b >> i) & 1u | (((p.b2 >> i) & 1u) << 1),
-                                           (p.c >> i) & 1u | (((p.c2 >> i) & 1u) << 1),
-                                           (p.d >> i) & 1u | (((p.d2 >> i) & 1u) << 1))];
-                }
-            }
-            nx = warp_sum32(nx);
-            ny = warp_sum32(ny);
-            nz = warp_sum32(nz);
-            nf = warp_sum32(nf);
+        if (tile >= num_scan_tiles) break;
+        const int64_t r0 = tile * kScanTile + (int64_t)threadIdx.x * kScanRowsPerThread;
+        uint4 c[kScanRowsPerThread];
+        unsigned long long sv = 0, sf = 0;
+#pragma unroll
+        for (int j = 0; j < kScanRowsPerThread; ++j) {
+            c[j] = (r0 + j < g.owned_rows) ? ws.rowv[r0 + j] : make_uint4(0, 0, 0, 0);
+            sv += (unsigned long long)c[j].x + c[j].y + c[j].z;
+            sf += c[j].w;
         }
-        if (lane == 0) {
-            s_cnt[warp][0] = nx;
-            s_cnt[warp][1] = ny;
-            s_cnt[warp][2] = nz;
-            s_cnt[warp][3] = nf;
+        const unsigned long long iv = warp_incl_scan64(sv, lane), jf = warp_incl_scan64(sf, lane);
+        if (lane == 31) {
+            s_warp[0][warp] = iv;
+            s_warp[1][warp] = jf;
         }
         __syncthreads();
-
-        if (warp < 2) {  // warp 0 scans vertex counts, warp 1 face counts
-            uint32_t mine = 0;
-            if (lane < kRowsPerTile) mine = warp == 0 ? s_cnt[lane][0] + s_cnt[lane][1] + s_cnt[lane][2] : s_cnt[lane][3];
-            const uint32_t incl = warp_incl_scan(mine, lane);
-            const unsigned long long aggregate = __shfl_sync(kFull, incl, 31);
-            const unsigned long long excl =
-                lookback(warp == 0 ? ws.status_v : ws.status_f, tile, aggregate, lane);
-            if (lane < kRowsPerTile) (warp == 0 ? s_rowv : s_rowf)[lane] = excl + incl - mine;
-            if (lane == 0 && tile == g.num_tiles - 1) {
-                if (warp == 0) ws.header->total_v = excl + aggregate;
-                else ws.header->total_f = excl + aggregate;
+        unsigned long long bv = 0, bf = 0, tv = 0, tf = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned long long a = s_warp[0][w], b = s_warp[1][w];
+            if (w < warp) {
+                bv += a;
+                bf += b;
+            }
+            tv += a;
+            tf += b;
+        }
+        if (warp < 2) {  // warp 0 looks back over vertex aggregates, warp 1 over face aggregates
+            const unsigned long long agg = warp == 0 ? tv : tf;
+            const unsigned long long e = lookback(warp == 0 ? ws.status_v : ws.status_f, tile, agg, lane);
+            if (lane == 0) {
+                s_excl[warp] = e;
+                if (tile == num_scan_tiles - 1) (warp == 0 ? ws.header->total_v : ws.header->total_f) = e + agg;
             }
         }
         __syncthreads();
-
-        if (lane == 0 && row < g.owned_rows) {
-            const uint32_t vx = (uint32_t)s_rowv[warp];
-            ws.rowv[row] = make_uint4(vx, vx + nx, vx + nx + ny, nf);
-            ws.rowf[row] = s_rowf[warp];
+        unsigned long long v = s_excl[0] + bv + iv - sv, f = s_excl[1] + bf + jf - sf;
+#pragma unroll
+        for (int j = 0; j < kScanRowsPerThread; ++j) {
+            if (r0 + j < g.owned_rows) {
+                const uint32_t vx = (uint32_t)v;
+                ws.rowv[r0 + j] = make_uint4(vx, vx + c[j].x, vx + c[j].x + c[j].y, c[j].w);
+                ws.rowf[r0 + j] = f;
+            }
+            v += (unsigned long long)c[j].x + c[j].y + c[j].z;
+            f += c[j].w;
         }
     }
 }
 
 void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
+    if (g.owned_rows <= 0) return;
     const int sms = sm_count();
-    if (g.num_tiles <= 0) return;
-    const int64_t cap = (int64_t)sms * 8;  // persistent CTAs; tiles are handed out by ticket
-    const int blocks = (int)(g.num_tiles < cap ? g.num_tiles : cap);
-    k_count_scan<<<blocks, kRowsPerTile * 32, 0, s>>>(g, ws);
+    {
+        const int64_t want = (g.owned_rows + 7) / 8, cap = (int64_t)sms * 8;
+        k_row_count<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g, ws);
+    }
+    {
+        const int64_t tiles = (g.owned_rows + kScanTile - 1) / kScanTile, cap = (int64_t)sms * 4;
+        k_row_scan<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(g, ws, tiles);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: emit vertices and faces.  Replaces gen_vertices_kernel (:70-138), gen_faces_kernel
 // (:140-209) and the two ATen passes of the bounding-box epilogue (:298).
+//
+// A warp owns a row; lane l owns word l of the current 1024-sample piece.  Two packed 64-bit
+// warp scans rank all eight crossing masks at once; the sparse work (one vertex per crossing
+// edge, one triangle per table entry) is compacted into shared-memory lists so that it runs one
+// item per lane with coalesced output stores.
 // ---------------------------------------------------------------------------------------------
 
 // Mask ids q used for edge ranking: which row's crossing mask numbers the edge.
@@ -267,47 +313,55 @@ void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
 //   q4 (x+1,y) z-edges q5 (x,y+1) x-edges q6 (x,y+1) z-edges q7 (x+1,y+1) z-edges
 // Cube edge e -> (q, dz) following the owner map of marching_cubes.cu:178-192:
 //   e: 0 1 2 3 4 5 6 7 8 9 10 11
-//   q: 0 3 5 1 0 3 5 1 2 4  7  6      dz = 1 for e in 4..7
+//   q: 0 3 5 1 0 3 5 1 2 4  7  6      dz = 1 for e in 4..7 (the edge sits at sample z+1)
 constexpr uint64_t kEdgeToMask = (0ull << 0) | (3ull << 3) | (5ull << 6) | (1ull << 9) | (0ull << 12) | (3ull << 15) |
                                  (5ull << 18) | (1ull << 21) | (2ull << 24) | (4ull << 27) | (7ull << 30) |
                                  (6ull << 33);
 
+#ifndef P3D_EMIT_MINBLOCKS
+#define P3D_EMIT_MINBLOCKS 4
+#endif
+constexpr int kTriBatch = 160;  // triangles of one batch of 32 cells (<= 5 each)
+
 struct WarpScratch {
-    uint32_t words[4][kPieceWords + 1];  // a, b, c, d (+ first word of the next piece)
-    uint32_t mask[8][kPieceWords];       // crossing masks q0..q7 of this piece
-    uint32_t base[8][kPieceWords + 1];   // id of the first crossing at/after word w, per mask
-    uint16_t list[kPieceWords * 32];     // compacted sample positions (vertex or cell work items)
+    uint4 words[kPieceWords];       // {a, b, c, d}
+    uint4 words2[kPieceWords];      // the same rows shifted by one sample (bit i = sample z+1)
+    uint2 rank[8][kPieceWords];     // per mask q and word: {crossing mask, id of its first crossing}
+    uint16_t list[kPieceWords * 32];  // compacted work items: vertex (z | axis<<10) or cell (z)
+    uint32_t tri[kTriBatch];        // z | three (q | dz<<3) nibbles << 10
 };
 
-__global__ void __launch_bounds__(kRowsPerTile * 32) k_emit(const float *__restrict__ grid, McGeom g, McWorkspace ws,
-                                                           McEmitParams prm, float *__restrict__ verts,
-                                                           int32_t *__restrict__ faces) {
-    __shared__ uint64_t s_table[256];
+__global__ void __launch_bounds__(kRowsPerTile * 32, P3D_EMIT_MINBLOCKS) k_emit(const float *__restrict__ grid, McGeom g, McWorkspace ws,
+                                                              McEmitParams prm, float *__restrict__ verts,
+                                                              int32_t *__restrict__ faces) {
+    __shared__ uint64_t s_table[256];  // per case: up to 15 nibbles (q | dz<<3), nibble 15 = #triangles
     __shared__ WarpScratch s_scratch[kRowsPerTile];
-    __shared__ unsigned int s_tile;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = c_case_table[i];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        const uint64_t t = c_case_table[c];
+        const uint32_t n = (uint32_t)(t >> 60);
+        uint64_t out = (uint64_t)n << 60;
+        for (uint32_t j = 0; j < 3 * n; ++j) {
+            const uint32_t e = (uint32_t)(t >> (4 * j)) & 15u;
+            const uint64_t nib = ((kEdgeToMask >> (3 * e)) & 7ull) | ((e & 12u) == 4u ? 8ull : 0ull);
+            out |= nib << (4 * j);
+        }
+        s_table[c] = out;
+    }
+    __syncthreads();
     WarpScratch &sc = s_scratch[warp];
     const int64_t plane = g.ry * g.rz;
+    const int64_t nwarps = (int64_t)gridDim.x * kRowsPerTile;
 
-    for (;;) {
-        __syncthreads();  // s_table ready / previous s_tile consumed
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ws.header->ticket_emit, 1u);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= g.num_tiles) break;
-        const int64_t row = tile * kRowsPerTile + warp;
-        if (row >= g.owned_rows) continue;
-
+    for (int64_t row = (int64_t)blockIdx.x * kRowsPerTile + warp; row < g.owned_rows; row += nwarps) {
         const RowPtrs r = row_ptrs(ws.bits, g, row);
         const bool cells = r.has_x && r.has_y;
-        const int64_t x = row / g.ry, y = row - x * g.ry;
-        const float fx = (float)(prm.x_origin + x);  // static_cast<float>(x), :107
-        const float fy = (float)y;
+        const float fx = (float)(prm.x_origin + r.x);  // static_cast<float>(x), :107
+        const float fy = (float)r.y;
         const float *grow = grid + row * g.rz;
 
-        // first ids of the four rows' vertex groups (row table written by K2 / halo import)
+        // first ids of the four rows' vertex groups (row table written by K2b / halo import)
         uint32_t run[8];
         {
             const uint4 t00 = ws.rowv[row];
@@ -341,71 +395,85 @@ __global__ void __launch_bounds__(kRowsPerTile * 32) k_emit(const float *__restr
             m[7] = cells ? ((p.c ^ p.c2) & zv) : 0u;
             const uint32_t act = active_cells(p, zv, cells);
 
+            // two packed scans (12-bit fields; a field's inclusive sum is <= 1024)
+            const unsigned long long ca = (unsigned long long)__popc(m[0]) | ((unsigned long long)__popc(m[1]) << 12) |
+                                          ((unsigned long long)__popc(m[2]) << 24) | ((unsigned long long)__popc(m[3]) << 36) |
+                                          ((unsigned long long)__popc(m[4]) << 48);
+            const unsigned long long cb = (unsigned long long)__popc(m[5]) | ((unsigned long long)__popc(m[6]) << 12) |
+                                          ((unsigned long long)__popc(m[7]) << 24) | ((unsigned long long)__popc(act) << 36);
+            const unsigned long long ia = warp_incl_scan64(ca, lane), ib = warp_incl_scan64(cb, lane);
+            const unsigned long long ta = __shfl_sync(kFull, ia, 31), tb = __shfl_sync(kFull, ib, 31);
+            const unsigned long long ea = ia - ca, eb = ib - cb;
+
             __syncwarp();  // the previous piece's readers are done with the scratch
-            sc.words[0][lane] = p.a;
-            sc.words[1][lane] = p.b;
-            sc.words[2][lane] = p.c;
-            sc.words[3][lane] = p.d;
-            if (lane == 31) {
-                sc.words[0][32] = p.an;
-                sc.words[1][32] = p.bn;
-                sc.words[2][32] = p.cn;
-                sc.words[3][32] = p.dn;
-            }
-            uint32_t ex[3], tot[3];  // exclusive rank / piece total of the own-row masks q0..q2
+            sc.words[lane] = make_uint4(p.a, p.b, p.c, p.d);
+            sc.words2[lane] = make_uint4(p.a2, p.b2, p.c2, p.d2);
+            uint32_t first[3], tot[3], ex[3];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const uint32_t cnt = __popc(m[q]);
-                const uint32_t incl = warp_incl_scan(cnt, lane);
-                const uint32_t total = __shfl_sync(kFull, incl, 31);
-                sc.mask[q][lane] = m[q];
-                sc.base[q][lane] = run[q] + incl - cnt;
-                if (lane == 31) sc.base[q][32] = run[q] + total;
+                const unsigned long long e = q < 5 ? ea : eb, t = q < 5 ? ta : tb;
+                const int sh = 12 * (q < 5 ? q : q - 5);
+                const uint32_t exq = (uint32_t)(e >> sh) & 0xfffu, totq = (uint32_t)(t >> sh) & 0xfffu;
+                sc.rank[q][lane] = make_uint2(m[q], run[q] + exq);
                 if (q < 3) {
-                    ex[q] = incl - cnt;
-                    tot[q] = total;
+                    first[q] = run[q];
+                    tot[q] = totq;
+                    ex[q] = exq;
                 }
-                run[q] += total;  // now the first id of the next piece
+                run[q] += totq;  // first id of the next piece
             }
+            const uint32_t ncell = (uint32_t)(tb >> 36) & 0xfffu;
+            const uint32_t cell_ex = (uint32_t)(eb >> 36) & 0xfffu;
 
             // ---- vertices on the row's own +x / +y / +z edges (gen_vertices_kernel) ----
+            // rounds: as many whole axis groups as fit the 1024-entry list (all three unless the
+            // piece is nearly all crossings)
+            for (int q0 = 0; q0 < 3;) {
+                uint32_t start[3] = {0, 0, 0};
+                uint32_t cnt = 0;
+                int q1 = q0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                uint32_t mm = m[q];
-                uint32_t pos = ex[q];
-                while (mm) {
-                    const int i = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    sc.list[pos++] = (uint16_t)((lane << 5) | i);
+                for (int q = 0; q < 3; ++q) {
+                    if (q == q1 && (q == q0 || cnt + tot[q] <= (uint32_t)(kPieceWords * 32))) {
+                        start[q] = cnt;
+                        uint32_t mm = m[q], pos = cnt + ex[q];
+                        while (mm) {
+                            const int i = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            sc.list[pos++] = (uint16_t)((lane << 5) | i | (q << 10));
+                        }
+                        cnt += tot[q];
+                        q1 = q + 1;
+                    }
                 }
                 __syncwarp();
-                const int64_t stride = q == 0 ? plane : (q == 1 ? g.rz : 1);
-                const uint32_t first = run[q] - tot[q];
-                for (uint32_t k = lane; k < tot[q]; k += 32) {
-                    const int64_t z = (int64_t)pc * (kPieceWords * 32) + sc.list[k];
+                for (uint32_t k = lane; k < cnt; k += 32) {
+                    const uint32_t ent = sc.list[k];
+                    const uint32_t ax = ent >> 10;
+                    const int64_t z = (int64_t)pc * (kPieceWords * 32) + (ent & 1023u);
+                    const int64_t stride = ax == 0 ? plane : (ax == 1 ? g.rz : 1);
                     const float d0 = __ldg(grow + z);
                     const float d1 = __ldg(grow + z + stride);
                     // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
                     const float dt = __fdiv_rn(__fsub_rn(prm.thresh, d0), __fsub_rn(d1, d0));
                     float px = fx, py = fy, pz = (float)z;
-                    if (q == 0) px = __fadd_rn(px, dt);
-                    if (q == 1) py = __fadd_rn(py, dt);
-                    if (q == 2) pz = __fadd_rn(pz, dt);
+                    if (ax == 0) px = __fadd_rn(px, dt);
+                    if (ax == 1) py = __fadd_rn(py, dt);
+                    if (ax == 2) pz = __fadd_rn(pz, dt);
+                    const uint32_t id = (ax == 0 ? first[0] - start[0] : (ax == 1 ? first[1] - start[1] : first[2] - start[2])) + k;
                     // vertices * scale + offset as two separately rounded ops (:298)
-                    float *out = verts + (int64_t)(first + k) * 3;
+                    float *out = verts + (int64_t)id * 3;
                     out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
                     out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
                     out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
                 }
                 __syncwarp();
+                q0 = q1;
             }
 
             // ---- faces of the row's cells, voxel-major, table order inside a cell (gen_faces_kernel) ----
-            {
-                const uint32_t cnt = __popc(act);
-                const uint32_t incl = warp_incl_scan(cnt, lane);
-                const uint32_t ncell = __shfl_sync(kFull, incl, 31);
-                uint32_t mm = act, pos = incl - cnt;
+            if (ncell) {
+                uint32_t mm = act, pos = cell_ex;
                 while (mm) {
                     const int i = __ffs(mm) - 1;
                     mm &= mm - 1;
@@ -413,28 +481,37 @@ __global__ void __launch_bounds__(kRowsPerTile * 32) k_emit(const float *__restr
                 }
                 __syncwarp();
                 for (uint32_t k0 = 0; k0 < ncell; k0 += 32) {
+                    // one cell per lane: case, triangle count, and one list entry per triangle
                     const uint32_t k = k0 + lane;
-                    const bool on = k < ncell;
-                    const int zl = on ? sc.list[k] : 0;
-                    const int wl = zl >> 5, i = zl & 31;
-                    const uint32_t ra = __funnelshift_r(sc.words[0][wl], sc.words[0][wl + 1], i) & 3u;
-                    const uint32_t rb = __funnelshift_r(sc.words[1][wl], sc.words[1][wl + 1], i) & 3u;
-                    const uint32_t rc = __funnelshift_r(sc.words[2][wl], sc.words[2][wl + 1], i) & 3u;
-                    const uint32_t rd = __funnelshift_r(sc.words[3][wl], sc.words[3][wl + 1], i) & 3u;
-                    uint64_t tt = on ? s_table[cube_case(ra, rb, rc, rd)] : 0ull;
-                    const uint32_t nt = (uint32_t)(tt >> 60);
-                    const uint32_t tincl = warp_incl_scan(nt, lane);
-                    int32_t *out = faces + (frun + (tincl - nt)) * 3ull;
-                    for (uint32_t j = 0; j < 3 * nt; ++j) {
-                        const uint32_t e = (uint32_t)tt & 15u;
-                        tt >>= 4;
-                        const uint32_t q = (uint32_t)(kEdgeToMask >> (3 * e)) & 7u;
-                        const int pz = i + ((e & 12u) == 4u ? 1 : 0);  // edges 4..7 sit at z+1
-                        const int w2 = wl + (pz >> 5), b2 = pz & 31;
-                        const uint32_t below = sc.mask[q][w2 & 31] & ((1u << b2) - 1u);  // b2 == 0 when w2 == 32
-                        out[j] = prm.vertex_id_base + (int32_t)(sc.base[q][w2] + __popc(below));
+                    uint32_t nt = 0, zl = 0;
+                    uint64_t tt = 0;
+                    if (k < ncell) {
+                        zl = sc.list[k];
+                        tt = s_table[cube_case_at(sc.words[zl >> 5], sc.words2[zl >> 5], zl & 31)];
+                        nt = (uint32_t)(tt >> 60);
                     }
-                    frun += __shfl_sync(kFull, tincl, 31);
+                    const uint32_t tincl = warp_incl_scan(nt, lane);
+                    const uint32_t btot = __shfl_sync(kFull, tincl, 31);
+                    uint32_t tp = tincl - nt;
+                    for (uint32_t t = 0; t < nt; ++t, tt >>= 12) sc.tri[tp++] = zl | (((uint32_t)tt & 0xfffu) << 10);
+                    __syncwarp();
+                    // one triangle per lane: rank its three edges, 12-byte coalesced stores
+                    for (uint32_t j = lane; j < btot; j += 32) {
+                        const uint32_t ent = sc.tri[j];
+                        const uint32_t wl = (ent >> 5) & 31u, i = ent & 31u;
+                        const uint32_t lt = (1u << i) - 1u;
+                        int32_t *out = faces + (frun + j) * 3ull;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t nib = (ent >> (10 + 4 * c)) & 15u;
+                            // crossings strictly below sample z (+dz): for dz = 1 the bit at z counts too; at
+                            // i = 31 that makes the whole word count, i.e. the first id of the next word
+                            const uint2 rk = sc.rank[nib & 7u][wl];
+                            out[c] = prm.vertex_id_base + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
+                        }
+                    }
+                    __syncwarp();
+                    frun += btot;
                 }
             }
         }
@@ -443,11 +520,10 @@ __global__ void __launch_bounds__(kRowsPerTile * 32) k_emit(const float *__restr
 
 void launch_emit(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
                  int32_t *faces, cudaStream_t s) {
+    if (g.owned_rows <= 0) return;
     const int sms = sm_count();
-    if (g.num_tiles <= 0) return;
-    const int64_t cap = (int64_t)sms * 4;
-    const int blocks = (int)(g.num_tiles < cap ? g.num_tiles : cap);
-    k_emit<<<blocks, kRowsPerTile * 32, 0, s>>>(grid, g, ws, p, verts, faces);
+    const int64_t want = (g.owned_rows + kRowsPerTile - 1) / kRowsPerTile, cap = (int64_t)sms * P3D_EMIT_MINBLOCKS;
+    k_emit<<<(unsigned)(want < cap ? want : cap), kRowsPerTile * 32, 0, s>>>(grid, g, ws, p, verts, faces);
 }
 
 // Multi-GPU: install the next shard's first-plane row table as this shard's halo-plane numbering.
