@@ -42,7 +42,8 @@ def build_core(force=False, verbose=False):
     if not force and not _stale(CORE_SO, _deps(CORE_SOURCES[:0]) + srcs):
         return CORE_SO
     t0 = time.time()
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", CORE_SO] + srcs
+    extra = os.environ.get("P3D_NVCC_EXTRA", "").split()  # e.g. -DP3D_STRIP_MINBLOCKS=2 for tuning runs
+    cmd = [NVCC] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", CORE_SO] + srcs
     subprocess.check_call(cmd)
     print(f"[build] {os.path.relpath(CORE_SO, ROOT)} in {time.time() - t0:.1f}s")
     return CORE_SO

@@ -2,6 +2,8 @@
 // Reference citations are into /root/reference/src/prim3d/Utility/marching_cubes.cu.
 #include "mc_kernels.cuh"
 
+#include <cstdlib>
+
 #include "mc_case_table.h"
 #include "scan_utils.cuh"
 
@@ -285,18 +287,6 @@ __global__ void __launch_bounds__(256) k_row_scan(McGeom g, McWorkspace ws, int6
     }
 }
 
-void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
-    if (g.owned_rows <= 0) return;
-    const int sms = sm_count();
-    {
-        const int64_t want = (g.owned_rows + 7) / 8, cap = (int64_t)sms * 8;
-        k_row_count<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g, ws);
-    }
-    {
-        const int64_t tiles = (g.owned_rows + kScanTile - 1) / kScanTile, cap = (int64_t)sms * 4;
-        k_row_scan<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(g, ws, tiles);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // K3: emit vertices and faces.  Replaces gen_vertices_kernel (:70-138), gen_faces_kernel
@@ -320,6 +310,9 @@ constexpr uint64_t kEdgeToMask = (0ull << 0) | (3ull << 3) | (5ull << 6) | (1ull
 
 #ifndef P3D_EMIT_MINBLOCKS
 #define P3D_EMIT_MINBLOCKS 4
+#endif
+#ifndef P3D_STRIP_MINBLOCKS
+#define P3D_STRIP_MINBLOCKS 3
 #endif
 constexpr int kTriBatch = 160;  // triangles of one batch of 32 cells (<= 5 each)
 
@@ -518,10 +511,380 @@ __global__ void __launch_bounds__(kRowsPerTile * 32, P3D_EMIT_MINBLOCKS) k_emit(
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Strip kernels (lane = row).  A warp owns a strip of 32 consecutive rows y0..y0+31 of one plane x
+// and walks their bit words in z order.  Each lane keeps the running ranks of ITS row in registers,
+// so no warp scans are needed to number crossings; the rows (x,y+1) / (x+1,y+1) a lane's cells
+// touch are simply the next lane's words (one shuffle; lane 31 loads row y0+32 itself).  Sparse
+// work from all 32 rows is pooled in shared memory and processed one item per lane.
+//   k_strip<false>  K2a: per-row counts {nx, ny, nz, nf}
+//   k_strip<true>   K3 : vertices and faces
+// ---------------------------------------------------------------------------------------------
+constexpr int kVRing = 128;   // vertex ring entries (a round adds <= 3 per lane, <= 31 are carried over)
+constexpr int kCellPool = 128;  // a round pools <= 4 cells per lane
+
+struct StripScratch {
+    uint4 words[32];            // per row-lane: {a, b, c, d} of the current word
+    uint4 words2[32];           // the same shifted by one sample
+    uint2 rank[8][32];          // per mask q and row-lane: {crossing mask, id of its first crossing}
+    unsigned long long fbase[32];  // per row-lane: index of the row's next face at the start of this word
+    uint32_t rowtris[32];       // per row-lane: triangles emitted so far for this word
+    uint2 vring[kVRing];        // pooled vertices {id, z<<7 | lane<<2 | axis}
+    uint32_t tri[kTriBatch];    // lane | bit<<5 | three (q|dz<<3) nibbles<<10 | offset in row<<22
+    uint16_t cell[kCellPool];   // lane<<5 | bit
+};
+
+__device__ __forceinline__ void load_group(const uint32_t *row, bool ok, int gw, int wz, bool vec, uint32_t out[4]) {
+    if (ok && vec && gw + 4 <= wz) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(row + gw));
+        out[0] = t.x;
+        out[1] = t.y;
+        out[2] = t.z;
+        out[3] = t.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = (ok && gw + j < wz) ? __ldg(row + gw + j) : 0u;
+    }
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256, EMIT ? P3D_STRIP_MINBLOCKS : 4)
+    k_strip(const float *__restrict__ grid, McGeom g, McWorkspace ws, McEmitParams prm, float *__restrict__ verts,
+            int32_t *__restrict__ faces) {
+    __shared__ uint64_t s_table[256];  // EMIT: nibbles (q | dz<<3), nibble 15 = #triangles; else only the counts are used
+    __shared__ StripScratch s_scratch[EMIT ? 8 : 1];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        const uint64_t t = c_case_table[c];
+        const uint32_t n = (uint32_t)(t >> 60);
+        uint64_t out = (uint64_t)n << 60;
+        for (uint32_t j = 0; j < 3 * n; ++j) {
+            const uint32_t e = (uint32_t)(t >> (4 * j)) & 15u;
+            out |= (((kEdgeToMask >> (3 * e)) & 7ull) | ((e & 12u) == 4u ? 8ull : 0ull)) << (4 * j);
+        }
+        s_table[c] = out;
+    }
+    __syncthreads();
+    StripScratch &sc = s_scratch[EMIT ? warp : 0];
+
+    const int wz = g.wz;
+    const bool vec = (wz & 3) == 0;
+    const int64_t plane = g.ry * g.rz;
+    const uint32_t nsy = (uint32_t)((g.ry + 31) / 32);
+    const int64_t nstrips = g.owned_x * (int64_t)nsy;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+
+    for (int64_t strip = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; strip < nstrips; strip += nwarps) {
+        int64_t x;
+        int64_t y0;
+        if (nstrips <= 0x7fffffffll) {
+            const uint32_t xs = (uint32_t)strip / nsy;
+            x = xs;
+            y0 = (int64_t)((uint32_t)strip - xs * nsy) * 32;
+        } else {
+            x = strip / nsy;
+            y0 = (strip - x * nsy) * 32;
+        }
+        const int64_t y = y0 + lane;
+        const bool valid = y < g.ry;
+        const bool has_x = x + 1 < g.rx;
+        const bool has_y = valid && (y + 1 < g.ry);
+        const uint32_t hx = (valid && has_x) ? 0xffffffffu : 0u;
+        const uint32_t hy = has_y ? 0xffffffffu : 0u;
+        const uint32_t hc = (has_x && has_y) ? 0xffffffffu : 0u;
+        const int64_t row = x * g.ry + y;
+        const uint32_t *pa = ws.bits + row * wz;
+        const uint32_t *pb = pa + g.ry * (int64_t)wz;
+        const bool halo = (lane == 31) && (y0 + 32 < g.ry);  // lane 31 also loads row y0+32
+
+        // per-row running state
+        uint32_t run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long frun = 0;
+        uint32_t nx = 0, ny = 0, nz = 0, nf = 0;
+        if (EMIT && valid) {
+            const uint4 t00 = ws.rowv[row];
+            run[0] = t00.x;
+            run[1] = t00.y;
+            run[2] = t00.z;
+            if (hc) {
+                const uint4 t10 = ws.rowv[row + g.ry], t01 = ws.rowv[row + 1], t11 = ws.rowv[row + g.ry + 1];
+                run[3] = t10.y;
+                run[4] = t10.z;
+                run[5] = t01.x;
+                run[6] = t01.z;
+                run[7] = t11.z;
+            }
+            frun = ws.rowf[row];
+        }
+        uint32_t vhead = 0, vcount = 0;  // vertex ring (warp-uniform)
+        const float fx = (float)(prm.x_origin + x);  // static_cast<float>(x), :107
+        const int64_t row0 = x * g.ry + y0;
+
+        auto flush_vertices = [&](uint32_t n) {  // the first n (<= 32) ring entries, one per lane
+            if ((uint32_t)lane < n) {
+                const uint2 ent = sc.vring[(vhead + lane) & (kVRing - 1)];
+                const uint32_t ax = ent.y & 3u, l = (ent.y >> 2) & 31u;
+                const int64_t z = ent.y >> 7;
+                const float *src = grid + (row0 + l) * g.rz + z;
+                const float d0 = __ldg(src);
+                const float d1 = __ldg(src + (ax == 0 ? plane : (ax == 1 ? g.rz : 1)));
+                // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
+                const float dt = __fdiv_rn(__fsub_rn(prm.thresh, d0), __fsub_rn(d1, d0));
+                float px = fx, py = (float)(y0 + l), pz = (float)z;
+                if (ax == 0) px = __fadd_rn(px, dt);
+                if (ax == 1) py = __fadd_rn(py, dt);
+                if (ax == 2) pz = __fadd_rn(pz, dt);
+                // vertices * scale + offset as two separately rounded ops (:298)
+                float *out = verts + (int64_t)ent.x * 3;
+                out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
+                out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
+                out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
+            }
+            vhead += n;
+            vcount -= n;
+        };
+
+        uint32_t na[4], nb[4], nd[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0};
+        load_group(pa, valid, 0, wz, vec, na);
+        load_group(pb, valid && has_x, 0, wz, vec, nb);
+        if (lane == 31) {
+            load_group(pa + wz, halo, 0, wz, vec, nd);
+            load_group(pb + wz, halo && has_x, 0, wz, vec, nc);
+        }
+
+        for (int gw = 0; gw < wz; gw += 4) {
+            uint32_t a[5], b[5], d[5], c[5];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[j] = na[j];
+                b[j] = nb[j];
+                d[j] = __shfl_down_sync(kFull, na[j], 1);
+                c[j] = __shfl_down_sync(kFull, nb[j], 1);
+                if (lane == 31) {
+                    d[j] = nd[j];
+                    c[j] = nc[j];
+                }
+            }
+            // prefetch the next group; its first word also closes this group's last word
+            load_group(pa, valid, gw + 4, wz, vec, na);
+            load_group(pb, valid && has_x, gw + 4, wz, vec, nb);
+            if (lane == 31) {
+                load_group(pa + wz, halo, gw + 4, wz, vec, nd);
+                load_group(pb + wz, halo && has_x, gw + 4, wz, vec, nc);
+            }
+            a[4] = na[0];
+            b[4] = nb[0];
+            d[4] = __shfl_down_sync(kFull, na[0], 1);
+            c[4] = __shfl_down_sync(kFull, nb[0], 1);
+            if (lane == 31) {
+                d[4] = nd[0];
+                c[4] = nc[0];
+            }
+
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = gw + j;
+                if (w >= wz) break;
+                const uint32_t zv = zvalid_mask(w, g.rz);
+                const uint32_t A = a[j], B = b[j], C = c[j], D = d[j];
+                const uint32_t A2 = __funnelshift_r(A, a[j + 1], 1), B2 = __funnelshift_r(B, b[j + 1], 1);
+                const uint32_t C2 = __funnelshift_r(C, c[j + 1], 1), D2 = __funnelshift_r(D, d[j + 1], 1);
+                uint32_t m[8];
+                m[0] = (A ^ B) & hx;        // :29-33  / :100-111
+                m[1] = (A ^ D) & hy;        // :35-39  / :113-124
+                m[2] = (A ^ A2) & zv;       // :41-45  / :126-137 (rows past ry hold zeros)
+                const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
+                const uint32_t act = (any & ~all) & zv & hc;  // :48 / :154
+                if (!EMIT) {
+                    nx += __popc(m[0]);
+                    ny += __popc(m[1]);
+                    nz += __popc(m[2]);
+                    uint32_t rem = act;
+                    const uint4 w4 = make_uint4(A, B, C, D), w42 = make_uint4(A2, B2, C2, D2);
+                    while (rem) {
+                        const int i = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        nf += (uint32_t)(s_table[cube_case_at(w4, w42, i)] >> 60);
+                    }
+                    continue;
+                }
+                m[3] = (B ^ C) & hc;
+                m[4] = (B ^ B2) & zv & hc;
+                m[5] = (D ^ C) & hc;
+                m[6] = (D ^ D2) & zv & hc;
+                m[7] = (C ^ C2) & zv & hc;
+                if (__any_sync(kFull, (m[0] | m[1] | m[2] | act) != 0u)) {  // else: nothing crosses in these 32x32 samples
+
+                // ---- vertices on the rows' own +x / +y / +z edges (gen_vertices_kernel) ----
+                {
+                    uint32_t r0 = m[0], r1 = m[1], r2 = m[2];
+                    uint32_t i0 = run[0], i1 = run[1], i2 = run[2];
+                    const uint32_t zb = (uint32_t)w << 5;
+                    for (;;) {
+                        const uint32_t have = __popc(r0) + __popc(r1) + __popc(r2);
+                        if (!__any_sync(kFull, have != 0u)) break;
+                        const uint32_t take = have < 3u ? have : 3u;
+                        const uint32_t incl = warp_incl_scan(take, lane);
+                        const uint32_t total = __shfl_sync(kFull, incl, 31);
+                        uint32_t pos = vhead + vcount + incl - take;
+                        for (uint32_t t = 0; t < take; ++t) {
+                            uint32_t id, code;
+                            if (r0) {
+                                const uint32_t i = __ffs(r0) - 1;
+                                r0 &= r0 - 1;
+                                id = i0++;
+                                code = ((zb + i) << 7) | (lane << 2) | 0u;
+                            } else if (r1) {
+                                const uint32_t i = __ffs(r1) - 1;
+                                r1 &= r1 - 1;
+                                id = i1++;
+                                code = ((zb + i) << 7) | (lane << 2) | 1u;
+                            } else {
+                                const uint32_t i = __ffs(r2) - 1;
+                                r2 &= r2 - 1;
+                                id = i2++;
+                                code = ((zb + i) << 7) | (lane << 2) | 2u;
+                            }
+                            sc.vring[(pos++) & (kVRing - 1)] = make_uint2(id, code);
+                        }
+                        vcount += total;
+                        __syncwarp();
+                        while (vcount >= 32u) flush_vertices(32u);
+                        __syncwarp();
+                    }
+                }
+
+                // ---- faces, voxel-major within each row, table order inside a cell (gen_faces_kernel) ----
+                if (__any_sync(kFull, act != 0u)) {
+                    sc.words[lane] = make_uint4(A, B, C, D);
+                    sc.words2[lane] = make_uint4(A2, B2, C2, D2);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sc.rank[q][lane] = make_uint2(m[q], run[q]);
+                    sc.fbase[lane] = frun;
+                    sc.rowtris[lane] = 0u;
+                    __syncwarp();
+                    uint32_t rem = act;
+                    for (;;) {
+                        const uint32_t have = __popc(rem);
+                        if (!__any_sync(kFull, have != 0u)) break;
+                        const uint32_t take = have < 4u ? have : 4u;
+                        const uint32_t incl = warp_incl_scan(take, lane);
+                        const uint32_t total = __shfl_sync(kFull, incl, 31);
+                        uint32_t pos = incl - take;
+                        for (uint32_t t = 0; t < take; ++t) {
+                            const uint32_t i = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            sc.cell[pos++] = (uint16_t)((lane << 5) | i);
+                        }
+                        __syncwarp();
+                        for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+                            // one cell per lane: case, triangle count, its offset among the row's triangles
+                            const uint32_t k = k0 + lane;
+                            const bool on = k < total;
+                            uint32_t nt = 0, cl = 32u + lane, bit = 0;
+                            uint64_t tt = 0;
+                            if (on) {
+                                const uint32_t e = sc.cell[k];
+                                cl = e >> 5;
+                                bit = e & 31u;
+                                tt = s_table[cube_case_at(sc.words[cl], sc.words2[cl], bit)];
+                                nt = (uint32_t)(tt >> 60);
+                            }
+                            const uint32_t tincl = warp_incl_scan(nt, lane);
+                            const uint32_t btot = __shfl_sync(kFull, tincl, 31);
+                            const uint32_t texcl = tincl - nt;
+                            const uint32_t peers = __match_any_sync(kFull, cl);   // cells of one row are contiguous
+                            const int head = __ffs(peers) - 1, tail = 31 - __clz(peers);
+                            const uint32_t rel = (on ? sc.rowtris[cl] : 0u) + texcl - __shfl_sync(kFull, texcl, head);
+                            __syncwarp();
+                            if (on && lane == tail) sc.rowtris[cl] = rel + nt;
+                            uint32_t tp = texcl;
+                            for (uint32_t t = 0; t < nt; ++t, tt >>= 12)
+                                sc.tri[tp++] = cl | (bit << 5) | (((uint32_t)tt & 0xfffu) << 10) | ((rel + t) << 22);
+                            __syncwarp();
+                            // one triangle per lane: rank its three edges, 12-byte stores
+                            for (uint32_t jj = lane; jj < btot; jj += 32) {
+                                const uint32_t ent = sc.tri[jj];
+                                const uint32_t tl = ent & 31u, i = (ent >> 5) & 31u;
+                                const uint32_t lt = (1u << i) - 1u;
+                                int32_t *out = faces + (sc.fbase[tl] + (ent >> 22)) * 3ull;
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    const uint32_t nib = (ent >> (10 + 4 * cc)) & 15u;
+                                    // crossings below sample z (+dz): for dz = 1 the bit at z counts too; at i = 31
+                                    // the whole word counts, i.e. the id of the first crossing of the next word
+                                    const uint2 rk = sc.rank[nib & 7u][tl];
+                                    out[cc] = prm.vertex_id_base + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    frun += sc.rowtris[lane];
+                    __syncwarp();
+                }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) run[q] += __popc(m[q]);
+            }
+        }
+        if (EMIT) {
+            __syncwarp();
+            if (vcount) flush_vertices(vcount);
+            __syncwarp();
+        } else if (valid) {
+            ws.rowv[row] = make_uint4(nx, ny, nz, nf);
+        }
+    }
+}
+
+// Kernel selection (measured on B200, gyroid 1024^3, profiles/r1c_*): counting is faster with the
+// lane = row strip kernel (0.35 ms vs 0.49 ms), emission with the warp-per-row kernel (1.6 ms vs
+// 3.9 ms: the strip variant scatters its 12-byte output stores over 32 rows and its unrolled body
+// misses the instruction cache).  P3D_MC_COUNT / P3D_MC_EMIT = row | strip override for A/B runs.
+static bool pick_strip(const char *var, bool dflt) {
+    const char *e = getenv(var);
+    if (!e || !e[0]) return dflt;
+    return e[0] == 's';
+}
+static bool use_strip_count() {
+    static const bool v = pick_strip("P3D_MC_COUNT", true);
+    return v;
+}
+static bool use_strip_emit() {
+    static const bool v = pick_strip("P3D_MC_EMIT", false);
+    return v;
+}
+
+void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
+    if (g.owned_rows <= 0) return;
+    const int sms = sm_count();
+    {
+        if (use_strip_count()) {
+            const int64_t strips = g.owned_x * ((g.ry + 31) / 32), want = (strips + 7) / 8, cap = (int64_t)sms * 4;
+            k_strip<false><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(nullptr, g, ws, McEmitParams{}, nullptr, nullptr);
+        } else {
+            const int64_t want = (g.owned_rows + 7) / 8, cap = (int64_t)sms * 8;
+            k_row_count<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g, ws);
+        }
+    }
+    {
+        const int64_t tiles = (g.owned_rows + kScanTile - 1) / kScanTile, cap = (int64_t)sms * 4;
+        k_row_scan<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(g, ws, tiles);
+    }
+}
+
 void launch_emit(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
                  int32_t *faces, cudaStream_t s) {
     if (g.owned_rows <= 0) return;
     const int sms = sm_count();
+    if (use_strip_emit()) {
+        const int64_t strips = g.owned_x * ((g.ry + 31) / 32), want = (strips + 7) / 8, cap = (int64_t)sms * P3D_STRIP_MINBLOCKS;
+        k_strip<true><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(grid, g, ws, p, verts, faces);
+        return;
+    }
     const int64_t want = (g.owned_rows + kRowsPerTile - 1) / kRowsPerTile, cap = (int64_t)sms * P3D_EMIT_MINBLOCKS;
     k_emit<<<(unsigned)(want < cap ? want : cap), kRowsPerTile * 32, 0, s>>>(grid, g, ws, p, verts, faces);
 }
