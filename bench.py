@@ -3,8 +3,9 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one full extraction (classify -> count/scan -> {V,F} readback -> output allocation
--> emit) of a synthetic gyroid SDF that is already resident in HBM.
+One "step" = one full extraction (tile pass: classify + count + look-back + vertices -> face-count
+scan -> {V,F} readback -> face allocation -> faces) of a synthetic gyroid SDF
+that is already resident in HBM.
 
   N = 1   gyroid 1024^3 fp32, BASELINE.json configs[2] (the HBM-roofline case)
   N > 1   gyroid 2048^3 fp32 sharded into dim-0 slabs with one halo plane, configs[4]; the total
@@ -197,7 +198,7 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     torch.cuda.synchronize()
 
-    launches_per_step = 3 + (1 if world > 1 and rank + 1 < world else 0)  # classify, count+scan, emit (+halo import)
+    launches_per_step = 3 + (1 if world > 1 and rank + 1 < world else 0)  # k_tile, k_fscan, k_faces (+halo import)
 
     def step():
         return sharded.marching_cubes_slab(slab, 0.0, x0, n)
@@ -285,8 +286,8 @@ def main():
     # ---- per-kernel timing on rank 0's slab (CUDA events on the launching stream) ----
     desc = capi.McDesc.make(slab.shape, 0.0, [0, 0, 0], [float(n)] * 3, owned_x=sharded.slab_range(n, world, 0)[1],
                             x_origin=0, global_rx=n)
-    V, F, ws = capi.mc_count(desc, slab)
-    verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+    V, F, ws, verts = capi.mc_count(desc, slab, vertex_capacity=sharded.capacity_for(slab.shape))
+    assert verts.shape[0] >= V
     faces = torch.empty((F, 3), dtype=torch.int32, device=dev)
     L = capi.lib()
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -304,19 +305,19 @@ def main():
             ts.append(a.elapsed_time(b))
         return statistics.mean(ts[2:])
 
-    stage = lambda k: capi.check(L.p3d_mc_debug_stage(ctypes.byref(desc), slab.data_ptr(), ws.data_ptr(), k, stream))
-    emit = lambda: capi.check(L.p3d_mc_emit(ctypes.byref(desc), slab.data_ptr(), ws.data_ptr(), verts.data_ptr(),
-                                            faces.data_ptr(), 0, stream))
+    stage = lambda k: capi.check(L.p3d_mc_debug_stage(ctypes.byref(desc), slab.data_ptr(), ws.data_ptr(), k,
+                                                      verts.data_ptr(), verts.shape[0], stream))
+    emit_faces = lambda: capi.check(L.p3d_mc_faces(ctypes.byref(desc), ws.data_ptr(), faces.data_ptr(), 0, stream))
     nvox = slab.numel()
-    k_ms = {"classify": time_kernel(lambda: stage(1)),
-            "count_scan": time_kernel(lambda: stage(2), before=lambda: stage(0)),
-            "emit": time_kernel(emit)}
-    k_bytes = {"classify": 4 * nvox, "count_scan": 0, "emit": 12 * V + 12 * F}
+    k_ms = {"tile_pass": time_kernel(lambda: stage(1), before=lambda: stage(0))}
+    k_ms["face_scan"] = time_kernel(lambda: stage(2), before=lambda: stage(0))
+    stage(0), stage(1), stage(2)   # a consistent workspace for the face pass
+    k_ms["faces"] = time_kernel(emit_faces)
+    k_bytes = {"tile_pass": 4 * nvox + 12 * V, "face_scan": 0, "faces": 12 * F}
     kernels = {k: {"ms": k_ms[k], "algorithmic_bytes": k_bytes[k], "achieved_gbs": k_bytes[k] / (k_ms[k] * 1e-3) / 1e9,
                    "share_of_step": k_ms[k] / sum(k_ms.values())} for k in k_ms}
     dom = max(k_ms, key=k_ms.get)
-    line["roofline"] = {"bound": "hbm", "kernel": {"classify": "k_classify_flat", "count_scan": "k_count_scan",
-                                                    "emit": "k_emit"}[dom],
+    line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "face_scan": "k_fscan", "faces": "k_faces"}[dom],
                         "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": k_bytes[dom], "launch_ms": k_ms[dom]}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 1
+#define P3D_ABI_VERSION 2
 
 typedef enum p3d_status {
     P3D_OK = 0,
@@ -48,16 +48,20 @@ const char *p3d_last_error(void);
  * The grid is float32, C-contiguous, idx = i*(ry*rz) + j*rz + k (marching_cubes.cu:20).
  * A sample is inside iff value > thresh (NaN and == thresh are outside).
  *
- * The reference needs the output sizes before it can allocate, and so do we; the call is
- * therefore split at the same place the reference synchronises (marching_cubes.cu:251-252):
+ * The reference needs the output sizes before it can allocate (it synchronises twice,
+ * marching_cubes.cu:251-252).  Here the grid is read ONCE: the pass that classifies and counts
+ * also writes the vertices, into a caller-provided buffer of speculative capacity, because the
+ * fp32 samples a vertex interpolates are on chip at that moment and nowhere else later:
  *
- *   p3d_mc_count()  classifies the grid once, builds the compact side products in the
- *                   workspace, and returns {V, F} to the host (one stream synchronise);
- *   p3d_mc_emit()   writes vertices float32 [V,3] and faces int32 [F,3] into caller-owned
- *                   buffers (asynchronous on `stream`).
+ *   p3d_mc_count()     one pass over the grid: inside bits, per-piece tables, {V, F} to the host
+ *                      (one stream synchronise) and every vertex whose id < vertex_capacity;
+ *   p3d_mc_vertices()  only needed when V > vertex_capacity: re-reads the grid and writes all
+ *                      vertices into an exact-size buffer (same ids, same values);
+ *   p3d_mc_faces()     faces int32 [F,3] from the side products alone (asynchronous).
  *
- * Output order is deterministic: vertices are numbered row by row ((x,y) rows in C order;
- * inside a row all x-edge vertices by z, then y-edge, then z-edge vertices), faces are in
+ * Output order is deterministic.  Vertices are numbered tile by tile (8 x 8 rows x 128 samples,
+ * in an order that depends on the grid shape only), inside a tile row by row, inside a row's
+ * 128-sample piece all x-edge vertices by z, then y-edge, then z-edge vertices.  Faces are in
  * voxel-major cell order with the triangle-table order inside a cell.  The reference's own
  * order is atomicAdd-arbitrary (marching_cubes.cu:104,117,130,199).
  *
@@ -77,38 +81,58 @@ typedef struct p3d_mc_desc {
     float upper[3];
 } p3d_mc_desc;
 
-/* Bytes of device workspace p3d_mc_count/p3d_mc_emit need for this descriptor
- * (1 bit per sample + 24 bytes per (x,y) row + scan state).  0 on invalid descriptor. */
+/* Bytes of device workspace for this descriptor (1 bit per sample + 20 bytes per 128 samples
+ * of a row + scan state; the reference's vertex_grids is 12 bytes per sample).  0 on an invalid
+ * descriptor. */
 size_t p3d_mc_workspace_bytes(const p3d_mc_desc *desc);
 
-/* counts_host[0] = V (vertices owned by this shard), counts_host[1] = F (faces of its cells).
- * Host memory.  Synchronises `stream`.  P3D_ERR_OVERFLOW if V > INT32_MAX. */
-p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace,
-                        size_t workspace_bytes, int64_t *counts_host, void *stream);
+/* A vertex capacity that covers smooth fields without a second pass: owned samples / 16
+ * (+ slack), never more than 3 per sample.  Callers that extract similar grids repeatedly
+ * should pass the previous V plus a margin instead. */
+int64_t p3d_mc_vertex_capacity_hint(const p3d_mc_desc *desc);
 
-/* vertices: float[3*V], faces: int32[3*F] (device).  Face indices are written as
- * vertex_id_base + local id (vertex_id_base = exclusive prefix of V over lower shards;
- * 0 on a single GPU).  Must follow p3d_mc_count on the same workspace and grid. */
-p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *workspace,
-                       float *vertices, int32_t *faces, int64_t vertex_id_base, void *stream);
+/* counts_host[0] = V (vertices owned by this shard), counts_host[1] = F (faces of its cells);
+ * host memory.  vertices: float[3*vertex_capacity] (device) or NULL with capacity 0; vertex i
+ * is written iff i < vertex_capacity, already scaled and offset (marching_cubes.cu:298), so
+ * the buffer is final when V <= vertex_capacity.  Synchronises `stream`.
+ * P3D_ERR_OVERFLOW if V > INT32_MAX. */
+p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace,
+                        size_t workspace_bytes, float *vertices, int64_t vertex_capacity,
+                        int64_t *counts_host, void *stream);
+
+/* vertices: float[3*vertex_capacity]; writes every vertex with id < vertex_capacity.  Must
+ * follow p3d_mc_count on the same workspace and grid.  Asynchronous. */
+p3d_status p3d_mc_vertices(const p3d_mc_desc *desc, const float *grid, void *workspace,
+                           float *vertices, int64_t vertex_capacity, void *stream);
+
+/* faces: int32[3*F] (device).  Face indices are written as vertex_id_base + local id
+ * (vertex_id_base = exclusive prefix of V over lower shards; 0 on a single GPU).  Must follow
+ * p3d_mc_count (and, for a slab with a halo plane, p3d_mc_import_halo_plane) on the same
+ * workspace.  Asynchronous. */
+p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t *faces,
+                        int64_t vertex_id_base, void *stream);
 
 /* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
- * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: classify, 2: count+scan.
- * The emit stage is p3d_mc_emit itself. */
+ * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: tile pass (classify,
+ * count, look-back, vertices), 2: face-count scan.  The face stage is p3d_mc_faces itself. */
 p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage,
-                              void *stream);
+                              float *vertices, int64_t vertex_capacity, void *stream);
 
-/* Multi-GPU halo exchange of vertex numbering (16 bytes per row of one plane):
- * export copies the row table of local plane 0 into table_out (uint32[4*ry], device);
- * import installs the next shard's exported table as the numbering of this shard's halo
- * plane, shifted by `delta` = this shard's V.  Both asynchronous on `stream`. */
+/* Multi-GPU halo exchange of vertex numbering (16 bytes per 128-sample piece of one plane):
+ * export copies the piece table of local plane 0 into table_out (uint32[
+ * p3d_mc_plane_table_words(desc)], device); import installs the next shard's exported table as
+ * the numbering of this shard's halo plane, shifted by `delta` = this shard's V.  Both
+ * asynchronous on `stream`. */
+int64_t p3d_mc_plane_table_words(const p3d_mc_desc *desc);
 p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *workspace,
                                      uint32_t *table_out, void *stream);
 p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace,
                                     const uint32_t *table_in, int64_t delta, void *stream);
 
-/* One-shot convenience for C/C++ callers: count, allocate through the callback, emit.
- * alloc(ctx, bytes) must return device memory on the current device (or NULL). */
+/* One-shot convenience for C/C++ callers: workspace and a vertex buffer of
+ * p3d_mc_vertex_capacity_hint() through the callback, count, faces (and an exact vertex buffer
+ * + p3d_mc_vertices if the hint was too small).  alloc(ctx, bytes) must return device memory on
+ * the current device (or NULL). */
 typedef void *(*p3d_alloc_fn)(void *ctx, size_t bytes);
 p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn alloc, void *alloc_ctx,
                       float **vertices, int32_t **faces, int64_t *num_vertices, int64_t *num_faces,

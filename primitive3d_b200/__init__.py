@@ -9,6 +9,6 @@ repository replaces: dense-grid marching cubes and marching tetrahedra.
 The reference-facing API is the sibling package `prim3d` (same names as the reference).
 There is no CPU implementation in this package; loading fails loudly if the library is unbuilt.
 """
-from .capi import McDesc, abi_version, lib, mc_count, mc_emit, mc_workspace_bytes  # noqa: F401
+from .capi import McDesc, abi_version, lib, mc_count, mc_faces, mc_vertices, mc_workspace_bytes  # noqa: F401
 
-__all__ = ["McDesc", "abi_version", "lib", "mc_count", "mc_emit", "mc_workspace_bytes"]
+__all__ = ["McDesc", "abi_version", "lib", "mc_count", "mc_faces", "mc_vertices", "mc_workspace_bytes"]

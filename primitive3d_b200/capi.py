@@ -51,12 +51,18 @@ def lib():
         L.p3d_last_error.restype = ctypes.c_char_p
         L.p3d_mc_workspace_bytes.restype = sz
         L.p3d_mc_workspace_bytes.argtypes = [dp]
+        L.p3d_mc_vertex_capacity_hint.restype = i64
+        L.p3d_mc_vertex_capacity_hint.argtypes = [dp]
+        L.p3d_mc_plane_table_words.restype = i64
+        L.p3d_mc_plane_table_words.argtypes = [dp]
         L.p3d_mc_count.restype = ctypes.c_int
-        L.p3d_mc_count.argtypes = [dp, vp, vp, sz, ctypes.POINTER(i64), vp]
-        L.p3d_mc_emit.restype = ctypes.c_int
-        L.p3d_mc_emit.argtypes = [dp, vp, vp, vp, vp, i64, vp]
+        L.p3d_mc_count.argtypes = [dp, vp, vp, sz, vp, i64, ctypes.POINTER(i64), vp]
+        L.p3d_mc_vertices.restype = ctypes.c_int
+        L.p3d_mc_vertices.argtypes = [dp, vp, vp, vp, i64, vp]
+        L.p3d_mc_faces.restype = ctypes.c_int
+        L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
-        L.p3d_mc_debug_stage.argtypes = [dp, vp, vp, ctypes.c_int, vp]
+        L.p3d_mc_debug_stage.argtypes = [dp, vp, vp, ctypes.c_int, vp, i64, vp]
         L.p3d_mc_export_first_plane.restype = ctypes.c_int
         L.p3d_mc_export_first_plane.argtypes = [dp, vp, vp, vp]
         L.p3d_mc_import_halo_plane.restype = ctypes.c_int
@@ -107,34 +113,51 @@ def mc_workspace_bytes(desc):
     return n
 
 
-def mc_count(desc, grid, workspace=None):
-    """-> (V, F, workspace).  Synchronises the current stream."""
+def mc_count(desc, grid, workspace=None, vertex_capacity=None):
+    """One pass over the grid -> (V, F, workspace, vbuf).
+
+    vbuf is a float32 [vertex_capacity, 3] tensor holding every vertex with id < vertex_capacity
+    (all of them when V <= vertex_capacity).  vertex_capacity=None asks the library for its hint,
+    0 writes no vertices.  Synchronises the current stream."""
     _grid_ok(grid)
     nbytes = mc_workspace_bytes(desc)
     if workspace is None:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
+    if vertex_capacity is None:
+        vertex_capacity = lib().p3d_mc_vertex_capacity_hint(ctypes.byref(desc))
+    vbuf = torch.empty((int(vertex_capacity), 3), dtype=torch.float32, device=grid.device)
     counts = (ctypes.c_int64 * 2)()
     with torch.cuda.device(grid.device):
         check(lib().p3d_mc_count(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), workspace.numel(),
-                                 counts, _stream()))
-    return counts[0], counts[1], workspace
+                                 vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity), counts, _stream()))
+    return counts[0], counts[1], workspace, vbuf
 
 
-def mc_emit(desc, grid, workspace, V, F, vertex_id_base=0):
-    """-> (vertices float32 [V,3], faces int32 [F,3]) on grid.device (asynchronous)."""
+def mc_vertices(desc, grid, workspace, V, vbuf=None):
+    """-> vertices float32 [V,3]: the speculative buffer of mc_count when it was large enough, otherwise an
+    exact-size buffer filled by the vertices-only second pass (asynchronous)."""
+    if vbuf is not None and vbuf.shape[0] >= V:
+        return vbuf[:V]
     verts = torch.empty((V, 3), dtype=torch.float32, device=grid.device)
-    faces = torch.empty((F, 3), dtype=torch.int32, device=grid.device)
     with torch.cuda.device(grid.device):
-        check(lib().p3d_mc_emit(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), verts.data_ptr(),
-                                faces.data_ptr(), int(vertex_id_base), _stream()))
-    return verts, faces
+        check(lib().p3d_mc_vertices(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), verts.data_ptr(), int(V),
+                                    _stream()))
+    return verts
 
 
-def marching_cubes(grid, thresh, lower=None, upper=None):
+def mc_faces(desc, workspace, F, vertex_id_base=0):
+    """-> faces int32 [F,3] on the workspace's device (asynchronous)."""
+    faces = torch.empty((F, 3), dtype=torch.int32, device=workspace.device)
+    with torch.cuda.device(workspace.device):
+        check(lib().p3d_mc_faces(ctypes.byref(desc), workspace.data_ptr(), faces.data_ptr(), int(vertex_id_base), _stream()))
+    return faces
+
+
+def marching_cubes(grid, thresh, lower=None, upper=None, vertex_capacity=None):
     """Single-GPU extraction through the C ABI (same outputs as prim3d.libPrim3D.marching_cubes)."""
     desc = McDesc.make(grid.shape, thresh, lower, upper)
-    V, F, ws = mc_count(desc, grid)
-    return mc_emit(desc, grid, ws, V, F)
+    V, F, ws, vbuf = mc_count(desc, grid, vertex_capacity=vertex_capacity)
+    return mc_vertices(desc, grid, ws, V, vbuf), mc_faces(desc, ws, F)
 
 
 def marching_tetrahedra(points, tets, sdf):

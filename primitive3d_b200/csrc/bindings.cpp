@@ -10,8 +10,13 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <algorithm>
+#include <array>
+#include <climits>
 #include <cstdio>
 #include <iostream>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -23,6 +28,9 @@ using torch::Tensor;
 
 #define P3D_CHECK_CUDA(x) TORCH_CHECK(x.is_cuda(), #x " must be a CUDA tensor")
 #define P3D_CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")
+
+std::mutex g_capacity_mutex;
+std::map<std::array<int64_t, 3>, int64_t> g_last_vertex_count;  // grid shape -> V of its last extraction
 
 void check_status(p3d_status st, const char *what) {
     TORCH_CHECK(st == P3D_OK, what, " failed (status ", static_cast<int>(st), "): ", p3d_last_error());
@@ -60,15 +68,42 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
     TORCH_CHECK(ws_bytes > 0, "marching_cubes: invalid grid shape");
     Tensor workspace = torch::empty({static_cast<int64_t>(ws_bytes)}, bytes_opt);
 
-    int64_t counts[2] = {0, 0};
-    check_status(p3d_mc_count(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), ws_bytes, counts, stream),
-                 "p3d_mc_count");
+    // The vertices are written by the same pass that counts them (the grid is read once), so their buffer
+    // is sized before V is known: the previous V of this grid shape plus a margin if there is one, else the
+    // library's hint.  A too-small guess costs a second, vertices-only pass; nothing else depends on it.
+    const std::array<int64_t, 3> key = {desc.rx, desc.ry, desc.rz};
+    int64_t cap = p3d_mc_vertex_capacity_hint(&desc);
+    {
+        std::lock_guard<std::mutex> lock(g_capacity_mutex);
+        auto it = g_last_vertex_count.find(key);
+        if (it != g_last_vertex_count.end()) cap = std::min<int64_t>(it->second + it->second / 16 + 4096, INT32_MAX);
+    }
+    Tensor vbuf = torch::empty({cap, 3}, density_grid.options());
 
-    Tensor vertices = torch::empty({counts[0], 3}, density_grid.options());
+    int64_t counts[2] = {0, 0};
+    check_status(p3d_mc_count(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), ws_bytes,
+                              vbuf.data_ptr<float>(), cap, counts, stream),
+                 "p3d_mc_count");
+    {
+        std::lock_guard<std::mutex> lock(g_capacity_mutex);
+        if (g_last_vertex_count.size() > 64) g_last_vertex_count.clear();
+        g_last_vertex_count[key] = counts[0];
+    }
+
+    Tensor vertices;
+    if (counts[0] <= cap) {
+        vertices = vbuf.narrow(0, 0, counts[0]);
+        // a view keeps the whole speculative buffer alive: copy out when most of it would be wasted
+        const int64_t wasted = (cap - counts[0]) * 12;
+        if (wasted > std::max<int64_t>(int64_t(64) << 20, counts[0] * 12)) vertices = vertices.clone();
+    } else {
+        vertices = torch::empty({counts[0], 3}, density_grid.options());
+        check_status(p3d_mc_vertices(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), vertices.data_ptr<float>(),
+                                     counts[0], stream),
+                     "p3d_mc_vertices");
+    }
     Tensor faces = torch::empty({counts[1], 3}, density_grid.options().dtype(torch::kInt));
-    check_status(p3d_mc_emit(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), vertices.data_ptr<float>(),
-                             faces.data_ptr<int32_t>(), 0, stream),
-                 "p3d_mc_emit");
+    check_status(p3d_mc_faces(&desc, workspace.data_ptr(), faces.data_ptr<int32_t>(), 0, stream), "p3d_mc_faces");
     // `workspace` is released to the caching allocator here; the allocator keeps it alive for the
     // kernels already queued on this stream.
     return {vertices, faces};

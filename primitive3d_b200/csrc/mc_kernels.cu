@@ -2,7 +2,10 @@
 // Reference citations are into /root/reference/src/prim3d/Utility/marching_cubes.cu.
 #include "mc_kernels.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
+
 #include <cstdlib>
+#include <cstring>
 
 #include "mc_case_table.h"
 #include "scan_utils.cuh"
@@ -14,546 +17,398 @@ namespace p3d {
 // persistent CTA because the per-cell lookups are lane-divergent.
 __constant__ uint64_t c_case_table[256] = P3D_MC_CASE_TABLE_INIT;
 
-// Bits z of word w that own a +z edge / a cell: z + 1 < rz.
-__device__ __forceinline__ uint32_t zvalid_mask(int w, int64_t rz) {
-    const int64_t n = rz - 1 - 32 * (int64_t)w;
+// Bits of word w (32 samples from z = 32*w) with z + 1 < rz: samples that own a +z edge / a cell.
+__device__ __forceinline__ uint32_t low_mask(int64_t n) {
     return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (int)n) - 1u));
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: classify.  inside = value > thresh  (marching_cubes.cu:25,31,37,43,50-57).
+// TMA / mbarrier plumbing (raw PTX; sm_100a).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Flat fast path (rz % 32 == 0, 16-byte aligned grid): a warp turns 1024 consecutive samples
-// (eight coalesced 512-byte float4 loads, all in flight together) into 32 bit words and
-// stores them as one 128-byte line.
-__global__ void __launch_bounds__(256) k_classify_flat(const float4 *__restrict__ g4, uint32_t *__restrict__ bits,
-                                                       int64_t nchunks, float thresh) {
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & 7;  // position inside the 8-lane group that assembles one word
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunks; c += nwarps) {
-        const float4 *p = g4 + c * 256 + lane;
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + u * 32);
-        uint32_t mine = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            uint32_t w = (v[u].x > thresh ? 1u : 0u) | (v[u].y > thresh ? 2u : 0u) | (v[u].z > thresh ? 4u : 0u) |
-                         (v[u].w > thresh ? 8u : 0u);
-            w <<= 4 * sub;
-            w |= __shfl_xor_sync(kFull, w, 1);
-            w |= __shfl_xor_sync(kFull, w, 2);
-            w |= __shfl_xor_sync(kFull, w, 4);
-            if (sub == u) mine = w;  // lane keeps word (u = sub, group = lane>>3)
-        }
-        bits[c * 32 + sub * 4 + (lane >> 3)] = mine;
-    }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 3-D tiled load global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
 }
 
-// General path (any rz / alignment): a warp handles 32 words of one row with scalar coalesced
-// loads and ballots; samples past the end of the row read as outside (pad bits are 0).
-__global__ void __launch_bounds__(256) k_classify_rows(const float *__restrict__ grid, uint32_t *__restrict__ bits,
-                                                       int64_t nrows, int64_t rz, int wz, int pieces, float thresh) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t items = nrows * pieces;
-    for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nwarps) {
-        const int64_t row = it / pieces;
-        const int p = (int)(it - row * pieces);
-        const float *src = grid + row * rz;
-        uint32_t mine = 0;
-#pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            bool in[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t z = ((int64_t)(p * 32 + j0 + u) << 5) + lane;
-                in[u] = (z < rz) && (__ldcs(src + (z < rz ? z : 0)) > thresh);
+// ---------------------------------------------------------------------------------------------
+// Pass A: k_tile.
+//
+// Shared memory of a CTA:
+//   stage[2]   fp32 samples of a tile: rows (xi, yi) of 0..8 x 0..8, kBoxZ samples each
+//   sbits      [81][8] words: inside bits of every staged row (word 4, bit 0 = the halo sample)
+//   s_piece    [64] vertex count of each owned (row, piece)
+//   s_list     compacted crossing edges of the tile: axis<<13 | row<<7 | z
+// A thread owns bit word (row r = tid>>2, word w = tid&3) of the tile in the count phase.
+// ---------------------------------------------------------------------------------------------
+constexpr int kListCap = 2048;
+constexpr int kSbitsStride = 8;
+constexpr int kRowPitch = kTileY + 1;  // staged rows per plane
+
+struct TileSmem {
+    uint32_t sbits[kBoxRows * kSbitsStride];
+    uint32_t piece[kTileX * kTileY];
+    uint16_t list[kListCap];
+    uint8_t ntri[256];  // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
+    unsigned long long bar[2];
+    unsigned long long tile_base;
+    int4 coord[2];      // {x0, y0, piece, -}
+    uint32_t tile[2];
+};
+constexpr int kTileSmemBytes = 2 * kStageBytes + (int)sizeof(TileSmem) + 128;
+
+template <bool TMA>
+__global__ void __launch_bounds__(kTileThreads, 2)
+    k_tile(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ grid, McGeom g, McWorkspace ws,
+           McEmitParams prm, float *__restrict__ verts, unsigned long long vcap, int mode) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    float *stage0 = reinterpret_cast<float *>(sm);
+    TileSmem &S = *reinterpret_cast<TileSmem *>(sm + 2 * kStageBytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ntiles = (uint32_t)g.ntiles;
+
+    // ntri by staged corner order: bit0 = corner 0 (a, z), bit1 = corner 4 (a, z+1), bit2 = corner 1 (b, z),
+    // bit3 = corner 5, bit4 = corner 2 (c, z), bit5 = corner 6, bit6 = corner 3 (d, z), bit7 = corner 7
+    // (corner numbering of marching_cubes.cu:50-57)
+    {
+        const uint32_t c = tid;
+        const uint32_t cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
+                            ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
+        S.ntri[c] = (uint8_t)(c_case_table[cs] >> 60);
+    }
+
+    // tile id -> coordinates; tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
+    // band x-block major, then y-block, then piece: the x halo plane of a block is re-read from L2, not HBM
+    auto fetch = [&](int st) {
+        const uint32_t t = atomicAdd(&ws.header->ticket, 1u);
+        S.tile[st] = t;
+        if (t >= ntiles) return;
+        const int64_t per_band = (int64_t)g.nxb * g.band * g.np;
+        const int64_t bi = (int64_t)t / per_band, rem = (int64_t)t - bi * per_band;
+        const int64_t left = g.nyb - bi * g.band, cur = left < g.band ? left : g.band;
+        const int64_t xb = rem / (cur * g.np), rem2 = rem - xb * (cur * g.np);
+        const int64_t yi = rem2 / g.np, p = rem2 - yi * g.np;
+        const int x0 = (int)(xb * kTileX), y0 = (int)((bi * g.band + yi) * kTileY);
+        S.coord[st] = make_int4(x0, y0, (int)p, 0);
+        if (TMA) {
+            const uint32_t bar = smem_u32(&S.bar[st]);
+            mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
+            tma_load_3d(smem_u32(sm + st * kStageBytes), &tmap, bar, (int)p * kTileZ, y0, x0);
+        }
+    };
+
+    if (tid == 0) {
+        if (TMA) {
+            mbar_init(smem_u32(&S.bar[0]), 1);
+            mbar_init(smem_u32(&S.bar[1]), 1);
+            mbar_fence_init();
+        }
+        fetch(0);
+        fetch(1);
+    }
+    __syncthreads();
+
+    const int64_t bstride = 4 * (int64_t)g.np;  // bit words per row
+    const float thresh = prm.thresh;
+
+    for (uint32_t it = 0;; ++it) {
+        const int st = it & 1;
+        const uint32_t tile = S.tile[st];
+        if (tile >= ntiles) break;
+        const int4 tc = S.coord[st];
+        const int x0 = tc.x, y0 = tc.y, p = tc.z;
+        const int64_t z0 = (int64_t)p * kTileZ;
+        float *tf = TMA ? reinterpret_cast<float *>(sm + st * kStageBytes) : stage0;
+
+        if (TMA) {
+            mbar_wait(smem_u32(&S.bar[st]), (it >> 1) & 1u);
+        } else {
+            for (int idx = tid; idx < kBoxRows * kBoxZ; idx += kTileThreads) {
+                const int r = idx / kBoxZ, c = idx - r * kBoxZ;
+                const int xi = r / kRowPitch, yi = r - xi * kRowPitch;
+                const int64_t gx = x0 + xi, gy = y0 + yi, gz = z0 + c;
+                tf[idx] = (gx < g.rx && gy < g.ry && gz < g.rz) ? __ldg(grid + (gx * g.ry + gy) * g.rz + gz) : 0.0f;
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t b = __ballot_sync(kFull, in[u]);
-                if (lane == j0 + u) mine = b;
+            __syncthreads();
+        }
+
+        // ---- phase 1: inside bits of the 81 staged rows.  inside = value > thresh (:25,31,37,43,50-57) ----
+        {
+            const int64_t nz = g.rz - z0;  // samples of this piece inside the grid (>= 1)
+            const bool ztail = nz < kTileZ;
+            const bool halo_ok = nz > kTileZ;
+            for (int r = warp; r < kBoxRows; r += kTileThreads / 32) {
+                const int xi = r / kRowPitch, yi = r - xi * kRowPitch;
+                const bool rowok = (x0 + xi < g.rx) && (y0 + yi < g.ry);
+                const float *src = tf + r * kBoxZ;
+                const float f0 = src[lane], f1 = src[lane + 32], f2 = src[lane + 64], f3 = src[lane + 96];
+                uint32_t b0 = __ballot_sync(kFull, f0 > thresh), b1 = __ballot_sync(kFull, f1 > thresh);
+                uint32_t b2 = __ballot_sync(kFull, f2 > thresh), b3 = __ballot_sync(kFull, f3 > thresh);
+                if (ztail) {
+                    b0 &= low_mask(nz);
+                    b1 &= low_mask(nz - 32);
+                    b2 &= low_mask(nz - 64);
+                    b3 &= low_mask(nz - 96);
+                }
+                if (!rowok) b0 = b1 = b2 = b3 = 0u;
+                if (lane == 0) {
+                    *reinterpret_cast<uint4 *>(&S.sbits[r * kSbitsStride]) = make_uint4(b0, b1, b2, b3);
+                    S.sbits[r * kSbitsStride + 4] = (rowok && halo_ok && src[kTileZ] > thresh) ? 1u : 0u;
+                }
             }
         }
-        const int w = p * 32 + lane;
-        if (w < wz) bits[row * wz + w] = mine;
-    }
-}
+        __syncthreads();
 
-void launch_classify(const float *grid, const McGeom &g, float thresh, uint32_t *bits, cudaStream_t s) {
-    const int sms = sm_count();
-    const int64_t nrows = g.rx * g.ry;
-    const int64_t n = nrows * g.rz;
-    const bool flat = (g.rz % 32 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
-    if (flat) {
-        const int64_t nchunks = n / 1024;
-        if (nchunks > 0) {
-            const int64_t want = (nchunks + 7) / 8;
-            const int blocks = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-            k_classify_flat<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(grid), bits, nchunks, thresh);
+        // ---- phase 2: crossing masks and counts of my word ----
+        const int r = tid >> 2, w = tid & 3;
+        const int xi = r >> 3, yi = r & 7;
+        const int ra = xi * kRowPitch + yi;
+        const int64_t x = x0 + xi, y = y0 + yi;
+        const bool inrow = (x < g.rx) && (y < g.ry);
+        const bool own = (x < g.owned_x) && (y < g.ry);
+        const bool hx = own && (x + 1 < g.rx), hy = own && (y + 1 < g.ry), hc = hx && hy;
+        const uint32_t *sa = &S.sbits[ra * kSbitsStride + w];
+        const uint32_t A = sa[0], An = sa[1];
+        const uint32_t B = sa[kRowPitch * kSbitsStride], Bn = sa[kRowPitch * kSbitsStride + 1];
+        const uint32_t D = sa[kSbitsStride], Dn = sa[kSbitsStride + 1];
+        const uint32_t C = sa[(kRowPitch + 1) * kSbitsStride], Cn = sa[(kRowPitch + 1) * kSbitsStride + 1];
+        const uint32_t A2 = __funnelshift_r(A, An, 1), B2 = __funnelshift_r(B, Bn, 1);
+        const uint32_t C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
+        const uint32_t zv = low_mask(g.rz - 1 - (z0 + 32 * w));
+        const uint32_t m0 = hx ? (A ^ B) : 0u;            // +x edges, :29-33 / :100-111
+        const uint32_t m1 = hy ? (A ^ D) : 0u;            // +y edges, :35-39 / :113-124
+        const uint32_t m2 = own ? ((A ^ A2) & zv) : 0u;   // +z edges, :41-45 / :126-137
+        uint32_t act = 0u;                                // cells with mixed corners, :48-66
+        if (hc) {
+            const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
+            act = (any & ~all) & zv;
         }
-        const int64_t rem = n - nchunks * 1024;  // a multiple of 32 samples, < 1024
-        if (rem > 0)
-            k_classify_rows<<<1, 32, 0, s>>>(grid + nchunks * 1024, bits + nchunks * 32, 1, rem, (int)(rem / 32), 1,
-                                             thresh);
-    } else {
-        const int64_t items = nrows * g.pieces;
-        const int64_t want = (items + 7) / 8;
-        const int blocks = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-        k_classify_rows<<<blocks, 256, 0, s>>>(grid, bits, nrows, g.rz, g.wz, g.pieces, thresh);
+        uint32_t nf = 0;
+        for (uint32_t rem = act; rem;) {
+            const int i = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const uint32_t code = (__funnelshift_r(A, An, i) & 3u) | ((__funnelshift_r(B, Bn, i) & 3u) << 2) |
+                                  ((__funnelshift_r(C, Cn, i) & 3u) << 4) | ((__funnelshift_r(D, Dn, i) & 3u) << 6);
+            nf += S.ntri[code];
+        }
+        // my (row, piece) = 4 adjacent lanes: packed {nx, ny, nz} (8-bit fields, <= 128 each)
+        const uint32_t cnt = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 8) | ((uint32_t)__popc(m2) << 16);
+        uint32_t inc = cnt;
+        {
+            uint32_t t = __shfl_up_sync(kFull, inc, 1);
+            if (w >= 1) inc += t;
+            t = __shfl_up_sync(kFull, inc, 2);
+            if (w >= 2) inc += t;
+        }
+        const uint32_t tot = __shfl_sync(kFull, inc, lane | 3);
+        const uint32_t exw = inc - cnt;
+        nf += __shfl_xor_sync(kFull, nf, 1);
+        nf += __shfl_xor_sync(kFull, nf, 2);
+        if (w == 0) S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
+
+        if (mode == 0) {
+            if (inrow) ws.bits[(x * g.ry + y) * bstride + 4 * p + w] = A;
+            if (own && w == 0) ws.nf[(x * g.ry + y) * g.np + p] = nf;
+            // the halo plane of a slab sits one past the last x-block when owned_x is a multiple of 8
+            if (tid < 32 && x0 + kTileX == g.owned_x && g.owned_x < g.rx) {
+                const int hy_ = tid >> 2, hw = tid & 3;
+                if (y0 + hy_ < g.ry)
+                    ws.bits[(g.owned_x * g.ry + y0 + hy_) * bstride + 4 * p + hw] =
+                        S.sbits[(kTileX * kRowPitch + hy_) * kSbitsStride + hw];
+            }
+        }
+        __syncthreads();
+
+        // ---- tile scan (every warp redundantly): first vertex of each (row, piece), relative to the tile ----
+        uint32_t vt, pe;
+        {
+            const uint32_t v0 = S.piece[2 * lane], v1 = S.piece[2 * lane + 1];
+            const uint32_t s2 = v0 + v1, incl = warp_incl_scan(s2, lane);
+            vt = __shfl_sync(kFull, incl, 31);
+            const uint32_t e0 = incl - s2, e1 = e0 + v0;
+            const uint32_t g0 = __shfl_sync(kFull, e0, r >> 1), g1 = __shfl_sync(kFull, e1, r >> 1);
+            pe = (r & 1) ? g1 : g0;
+        }
+        const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
+        const uint32_t wfirst[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
+        const uint32_t wmask[3] = {m0, m1, m2};
+
+        // ---- first vertex id of the tile: decoupled look-back over tiles (warp 0) ----
+        if (warp == 0) {
+            unsigned long long tb;
+            if (mode == 0) {
+                tb = lookback(ws.status, (int64_t)tile, (unsigned long long)vt, lane);
+                if (lane == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
+            } else {
+                tb = tile ? (ws.status[tile - 1] & kValueMask) : 0ull;
+            }
+            if (lane == 0) S.tile_base = tb;
+        }
+
+        // ---- vertices: compact the crossing edges, then one edge per thread (gen_vertices_kernel :70-138) ----
+        for (uint32_t c0 = 0; c0 < vt || c0 == 0; c0 += kListCap) {
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                uint32_t pos = wfirst[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
+                for (uint32_t rem = wmask[ax]; rem; ++pos) {
+                    const int i = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    if (pos < (uint32_t)kListCap) S.list[pos] = (uint16_t)((ax << 13) | (r << 7) | (w << 5) | i);
+                }
+            }
+            __syncthreads();  // list complete; S.tile_base visible
+            const unsigned long long tb = S.tile_base;
+            if (c0 == 0 && mode == 0 && own && w == 0)
+                ws.ptab[(x * g.ry + y) * g.np + p] =
+                    make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
+            const uint32_t n = vt - c0 < (uint32_t)kListCap ? vt - c0 : (uint32_t)kListCap;
+            for (uint32_t k = tid; k < n && vt > c0; k += kTileThreads) {
+                const unsigned long long id = tb + c0 + k;
+                if (id >= vcap) continue;
+                const uint32_t ent = S.list[k];
+                const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
+                const uint32_t exi = er >> 3, eyi = er & 7u;
+                const float *src = tf + (exi * kRowPitch + eyi) * kBoxZ + ez;
+                const float d0 = src[0];
+                const float d1 = src[ax == 0 ? kRowPitch * kBoxZ : (ax == 1 ? kBoxZ : 1)];
+                // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
+                const float dt = __fdiv_rn(__fsub_rn(thresh, d0), __fsub_rn(d1, d0));
+                float px = (float)(prm.x_origin + x0 + (int)exi);  // static_cast<float>(x), :107
+                float py = (float)(y0 + (int)eyi);
+                float pz = (float)(z0 + ez);
+                if (ax == 0) px = __fadd_rn(px, dt);
+                if (ax == 1) py = __fadd_rn(py, dt);
+                if (ax == 2) pz = __fadd_rn(pz, dt);
+                // vertices * scale + offset as two separately rounded ops (:298)
+                float *out = verts + id * 3ull;
+                out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
+                out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
+                out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
+            }
+            __syncthreads();  // the list (next chunk) and the stage (next tile) may be overwritten
+        }
+
+        if (tid == 0) fetch(st);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared row machinery of K2 and K3.
-// A warp owns row r = (x,y).  Lane l holds word w = 32*piece + l of the four bit rows
-//   a = (x,y)  b = (x+1,y)  c = (x+1,y+1)  d = (x,y+1)
-// i.e. the reference's cube corners 0,1,2,3 at z and 4,5,6,7 at z+1 (marching_cubes.cu:50-57).
+// k_fscan: exclusive scan of the per-piece triangle counts in voxel-major (row, piece) order --
+// single pass, decoupled look-back over tiles of 2048 pieces.  f8[i] = index of the first face of
+// piece 8*i; the grand total goes to the header.
 // ---------------------------------------------------------------------------------------------
-struct RowPtrs {
-    const uint32_t *a, *b, *c, *d;
-    bool has_x, has_y;  // x+1 < rx, y+1 < ry
-    int64_t x, y;
+__global__ void __launch_bounds__(256) k_fscan(McGeom g, McWorkspace ws) {
+    __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_excl;
+    __shared__ unsigned int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&ws.header->ticket_scan, 1u);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= g.nscan) break;
+        const int64_t r0 = tile * kFscanTile + (int64_t)threadIdx.x * 8;
+        uint32_t c[8];
+        if (r0 + 8 <= g.npieces) {
+            const uint4 lo = *reinterpret_cast<const uint4 *>(ws.nf + r0), hi = *reinterpret_cast<const uint4 *>(ws.nf + r0 + 4);
+            c[0] = lo.x, c[1] = lo.y, c[2] = lo.z, c[3] = lo.w, c[4] = hi.x, c[5] = hi.y, c[6] = hi.z, c[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = (r0 + j < g.npieces) ? ws.nf[r0 + j] : 0u;
+        }
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += c[j];
+        const unsigned long long incl = warp_incl_scan64(sum, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned long long a = s_warp[k];
+            if (k < warp) before += a;
+            total += a;
+        }
+        if (warp == 0) {
+            const unsigned long long e = lookback(ws.status_f, tile, total, lane);
+            if (lane == 0) {
+                s_excl = e;
+                if (tile == g.nscan - 1) ws.header->total_f = e + total;
+            }
+        }
+        __syncthreads();
+        if (r0 < g.npieces) ws.f8[r0 >> 3] = s_excl + before + incl - sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass B: k_faces.  Replaces gen_faces_kernel (:140-209).
+//
+// A warp takes 32 consecutive (row, piece) pairs in voxel-major order; lane l owns the 128 cells of
+// piece l.  It recomputes the eight crossing masks of each of its four words,
+//   q0 (x,y) x-edges   q1 (x,y) y-edges   q2 (x,y) z-edges   q3 (x+1,y) y-edges
+//   q4 (x+1,y) z-edges q5 (x,y+1) x-edges q6 (x,y+1) z-edges q7 (x+1,y+1) z-edges
+// carries the id of the first crossing of each mask along the piece (table entry + popcounts), and
+// parks {corner words, masks, first ids} of every word with active cells in shared memory.  The sparse
+// work then runs lane-balanced: one active cell per lane (case, triangle count), one triangle per lane
+// (three ranks, 12-byte store).  Cube edge e -> (q, dz) follows the owner map of :178-192:
+//   e: 0 1 2 3 4 5 6 7 8 9 10 11
+//   q: 0 3 5 1 0 3 5 1 2 4  7  6      dz = 1 for e in 4..7 (the edge sits at sample z+1)
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kEdgeToMask = (0ull << 0) | (3ull << 3) | (5ull << 6) | (1ull << 9) | (0ull << 12) | (3ull << 15) |
+                                 (5ull << 18) | (1ull << 21) | (2ull << 24) | (4ull << 27) | (7ull << 30) |
+                                 (6ull << 33);
+constexpr int kFaceWarps = 4;
+constexpr int kCellCap = 1024;
+constexpr int kTriBatch = 160;  // triangles of one batch of 32 cells (<= 5 each)
+
+struct FaceScratch {
+    uint4 corner[kFaceGroup * 4][2];  // per word slot: {a, b, c, d} at z and at z+1
+    uint2 rm[kFaceGroup * 4][8];      // per word slot and mask q: {crossing mask, id of its first crossing}
+    uint16_t cell[kCellCap];          // slot<<5 | bit
+    uint32_t tri[kTriBatch];          // slot<<5 | bit | three (q | dz<<3) nibbles << 12
 };
 
-__device__ __forceinline__ RowPtrs row_ptrs(const uint32_t *bits, const McGeom &g, int64_t row) {
-    RowPtrs r;
-    int64_t x, y;
-    if (g.rx * g.ry <= 0x7fffffffll) {
-        x = (uint32_t)row / (uint32_t)g.ry;
-        y = (uint32_t)row - (uint32_t)x * (uint32_t)g.ry;
-    } else {
-        x = row / g.ry;
-        y = row - x * g.ry;
-    }
-    r.has_x = x + 1 < g.rx;
-    r.has_y = y + 1 < g.ry;
-    r.a = bits + row * g.wz;
-    r.b = r.a + (r.has_x ? g.ry * (int64_t)g.wz : 0);
-    r.d = r.a + (r.has_y ? g.wz : 0);
-    r.c = r.b + (r.has_y ? g.wz : 0);
-    r.x = x;
-    r.y = y;
-    return r;
-}
+constexpr int kFaceSmemBytes = 256 * (int)sizeof(uint64_t) + kFaceWarps * (int)sizeof(FaceScratch);
 
-struct Piece {
-    uint32_t a, b, c, d;      // this lane's words
-    uint32_t a2, b2, c2, d2;  // the same rows shifted down by one sample: bit i = sample z+1
-    uint32_t an, bn, cn, dn;  // next words (lane+1's; lane 31 loads them)
-};
-
-__device__ __forceinline__ uint32_t next_word(const uint32_t *row, uint32_t mine, int w, int wz, int lane) {
-    uint32_t n = __shfl_down_sync(kFull, mine, 1);
-    if (lane == 31) n = (w + 1 < wz) ? __ldg(row + w + 1) : 0u;
-    return n;
-}
-
-__device__ __forceinline__ Piece load_piece(const RowPtrs &r, int w, int wz, int lane) {
-    Piece p;
-    const bool in = w < wz;
-    p.a = in ? __ldg(r.a + w) : 0u;
-    p.b = in ? __ldg(r.b + w) : 0u;
-    p.c = in ? __ldg(r.c + w) : 0u;
-    p.d = in ? __ldg(r.d + w) : 0u;
-    p.an = next_word(r.a, p.a, w, wz, lane);
-    p.bn = next_word(r.b, p.b, w, wz, lane);
-    p.cn = next_word(r.c, p.c, w, wz, lane);
-    p.dn = next_word(r.d, p.d, w, wz, lane);
-    p.a2 = (p.a >> 1) | (p.an << 31);
-    p.b2 = (p.b >> 1) | (p.bn << 31);
-    p.c2 = (p.c >> 1) | (p.cn << 31);
-    p.d2 = (p.d >> 1) | (p.dn << 31);
-    return p;
-}
-
-// Cells of the row whose 8 corners are not all equal (z+1 < rz, x+1 < rx, y+1 < ry).
-__device__ __forceinline__ uint32_t active_cells(const Piece &p, uint32_t zv, bool cells) {
-    const uint32_t any = p.a | p.b | p.c | p.d | p.a2 | p.b2 | p.c2 | p.d2;
-    const uint32_t all = p.a & p.b & p.c & p.d & p.a2 & p.b2 & p.c2 & p.d2;
-    return cells ? ((any & ~all) & zv) : 0u;
-}
-
-// 8-bit cube case of the cell at bit i (corner order of marching_cubes.cu:168-176) from the packed
-// words {a,b,c,d} and their one-sample-shifted copies
+// 8-bit cube case of the cell at bit i (corner order of :168-176)
 __device__ __forceinline__ uint32_t cube_case_at(const uint4 &w, const uint4 &w2, int i) {
     return ((w.x >> i) & 1u) | (((w.y >> i) & 1u) << 1) | (((w.z >> i) & 1u) << 2) | (((w.w >> i) & 1u) << 3) |
            (((w2.x >> i) & 1u) << 4) | (((w2.y >> i) & 1u) << 5) | (((w2.z >> i) & 1u) << 6) | (((w2.w >> i) & 1u) << 7);
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2a: per-row counts from the bit words.  Replaces count_vertices_faces_kernel (:4-68) and its
-// two global atomic counters.  rowv[row] = {nx, ny, nz, nf} (turned into offsets by K2b).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_row_count(McGeom g, McWorkspace ws) {
-    __shared__ uint8_t s_ntri[256];
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = (uint8_t)(c_case_table[i] >> 60);
-    __syncthreads();
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < g.owned_rows; row += nwarps) {
-        const RowPtrs r = row_ptrs(ws.bits, g, row);
-        const bool cells = r.has_x && r.has_y;
-        uint32_t nx = 0, ny = 0, nz = 0, nf = 0;
-        for (int pc = 0; pc < g.pieces; ++pc) {
-            const int w = pc * kPieceWords + lane;
-            const Piece p = load_piece(r, w, g.wz, lane);
-            const uint32_t zv = zvalid_mask(w, g.rz);
-            if (r.has_x) nx += __popc(p.a ^ p.b);       // :29-33
-            if (r.has_y) ny += __popc(p.a ^ p.d);       // :35-39
-            nz += __popc((p.a ^ p.a2) & zv);            // :41-45
-            uint32_t act = active_cells(p, zv, cells);  // :48-66
-            const uint4 w4 = make_uint4(p.a, p.b, p.c, p.d), w42 = make_uint4(p.a2, p.b2, p.c2, p.d2);
-            while (act) {
-                const int i = __ffs(act) - 1;
-                act &= act - 1;
-                nf += s_ntri[cube_case_at(w4, w42, i)];
-            }
-        }
-        // one packed reduction: nx,ny,nz <= rz (< 2^31 / 32 per lane) ... keep them separate but cheap
-        const unsigned long long lo = warp_sum64(((unsigned long long)ny << 32) | nx);
-        const unsigned long long hi = warp_sum64(((unsigned long long)nf << 32) | nz);
-        if (lane == 0) ws.rowv[row] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2b: exclusive scan of the per-row counts -- single pass, decoupled look-back over tiles of
-// 2048 rows (no CUB / thrust).  rowv[row] becomes {vx, vy, vz, nf}: first vertex id of the row's
-// x-, y- and z-edge groups; rowf[row] = first face of the row.  Totals go to the header.
-// ---------------------------------------------------------------------------------------------
-constexpr int kScanRowsPerThread = 8;
-constexpr int kScanTile = 256 * kScanRowsPerThread;
-
-__global__ void __launch_bounds__(256) k_row_scan(McGeom g, McWorkspace ws, int64_t num_scan_tiles) {
-    __shared__ unsigned long long s_warp[2][8];
-    __shared__ unsigned long long s_excl[2];
-    __shared__ unsigned int s_tile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ws.header->ticket, 1u);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= num_scan_tiles) break;
-        const int64_t r0 = tile * kScanTile + (int64_t)threadIdx.x * kScanRowsPerThread;
-        uint4 c[kScanRowsPerThread];
-        unsigned long long sv = 0, sf = 0;
-#pragma unroll
-        for (int j = 0; j < kScanRowsPerThread; ++j) {
-            c[j] = (r0 + j < g.owned_rows) ? ws.rowv[r0 + j] : make_uint4(0, 0, 0, 0);
-            sv += (unsigned long long)c[j].x + c[j].y + c[j].z;
-            sf += c[j].w;
-        }
-        const unsigned long long iv = warp_incl_scan64(sv, lane), jf = warp_incl_scan64(sf, lane);
-        if (lane == 31) {
-            s_warp[0][warp] = iv;
-            s_warp[1][warp] = jf;
-        }
-        __syncthreads();
-        unsigned long long bv = 0, bf = 0, tv = 0, tf = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const unsigned long long a = s_warp[0][w], b = s_warp[1][w];
-            if (w < warp) {
-                bv += a;
-                bf += b;
-            }
-            tv += a;
-            tf += b;
-        }
-        if (warp < 2) {  // warp 0 looks back over vertex aggregates, warp 1 over face aggregates
-            const unsigned long long agg = warp == 0 ? tv : tf;
-            const unsigned long long e = lookback(warp == 0 ? ws.status_v : ws.status_f, tile, agg, lane);
-            if (lane == 0) {
-                s_excl[warp] = e;
-                if (tile == num_scan_tiles - 1) (warp == 0 ? ws.header->total_v : ws.header->total_f) = e + agg;
-            }
-        }
-        __syncthreads();
-        unsigned long long v = s_excl[0] + bv + iv - sv, f = s_excl[1] + bf + jf - sf;
-#pragma unroll
-        for (int j = 0; j < kScanRowsPerThread; ++j) {
-            if (r0 + j < g.owned_rows) {
-                const uint32_t vx = (uint32_t)v;
-                ws.rowv[r0 + j] = make_uint4(vx, vx + c[j].x, vx + c[j].x + c[j].y, c[j].w);
-                ws.rowf[r0 + j] = f;
-            }
-            v += (unsigned long long)c[j].x + c[j].y + c[j].z;
-            f += c[j].w;
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// K3: emit vertices and faces.  Replaces gen_vertices_kernel (:70-138), gen_faces_kernel
-// (:140-209) and the two ATen passes of the bounding-box epilogue (:298).
-//
-// A warp owns a row; lane l owns word l of the current 1024-sample piece.  Two packed 64-bit
-// warp scans rank all eight crossing masks at once; the sparse work (one vertex per crossing
-// edge, one triangle per table entry) is compacted into shared-memory lists so that it runs one
-// item per lane with coalesced output stores.
-// ---------------------------------------------------------------------------------------------
-
-// Mask ids q used for edge ranking: which row's crossing mask numbers the edge.
-//   q0 (x,y) x-edges   q1 (x,y) y-edges   q2 (x,y) z-edges   q3 (x+1,y) y-edges
-//   q4 (x+1,y) z-edges q5 (x,y+1) x-edges q6 (x,y+1) z-edges q7 (x+1,y+1) z-edges
-// Cube edge e -> (q, dz) following the owner map of marching_cubes.cu:178-192:
-//   e: 0 1 2 3 4 5 6 7 8 9 10 11
-//   q: 0 3 5 1 0 3 5 1 2 4  7  6      dz = 1 for e in 4..7 (the edge sits at sample z+1)
-constexpr uint64_t kEdgeToMask = (0ull << 0) | (3ull << 3) | (5ull << 6) | (1ull << 9) | (0ull << 12) | (3ull << 15) |
-                                 (5ull << 18) | (1ull << 21) | (2ull << 24) | (4ull << 27) | (7ull << 30) |
-                                 (6ull << 33);
-
-#ifndef P3D_EMIT_MINBLOCKS
-#define P3D_EMIT_MINBLOCKS 4
-#endif
-#ifndef P3D_STRIP_MINBLOCKS
-#define P3D_STRIP_MINBLOCKS 3
-#endif
-constexpr int kTriBatch = 160;  // triangles of one batch of 32 cells (<= 5 each)
-
-struct WarpScratch {
-    uint4 words[kPieceWords];       // {a, b, c, d}
-    uint4 words2[kPieceWords];      // the same rows shifted by one sample (bit i = sample z+1)
-    uint2 rank[8][kPieceWords];     // per mask q and word: {crossing mask, id of its first crossing}
-    uint16_t list[kPieceWords * 32];  // compacted work items: vertex (z | axis<<10) or cell (z)
-    uint32_t tri[kTriBatch];        // z | three (q | dz<<3) nibbles << 10
-};
-
-__global__ void __launch_bounds__(kRowsPerTile * 32, P3D_EMIT_MINBLOCKS) k_emit(const float *__restrict__ grid, McGeom g, McWorkspace ws,
-                                                              McEmitParams prm, float *__restrict__ verts,
-                                                              int32_t *__restrict__ faces) {
-    __shared__ uint64_t s_table[256];  // per case: up to 15 nibbles (q | dz<<3), nibble 15 = #triangles
-    __shared__ WarpScratch s_scratch[kRowsPerTile];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
-        const uint64_t t = c_case_table[c];
-        const uint32_t n = (uint32_t)(t >> 60);
-        uint64_t out = (uint64_t)n << 60;
-        for (uint32_t j = 0; j < 3 * n; ++j) {
-            const uint32_t e = (uint32_t)(t >> (4 * j)) & 15u;
-            const uint64_t nib = ((kEdgeToMask >> (3 * e)) & 7ull) | ((e & 12u) == 4u ? 8ull : 0ull);
-            out |= nib << (4 * j);
-        }
-        s_table[c] = out;
-    }
-    __syncthreads();
-    WarpScratch &sc = s_scratch[warp];
-    const int64_t plane = g.ry * g.rz;
-    const int64_t nwarps = (int64_t)gridDim.x * kRowsPerTile;
-
-    for (int64_t row = (int64_t)blockIdx.x * kRowsPerTile + warp; row < g.owned_rows; row += nwarps) {
-        const RowPtrs r = row_ptrs(ws.bits, g, row);
-        const bool cells = r.has_x && r.has_y;
-        const float fx = (float)(prm.x_origin + r.x);  // static_cast<float>(x), :107
-        const float fy = (float)r.y;
-        const float *grow = grid + row * g.rz;
-
-        // first ids of the four rows' vertex groups (row table written by K2b / halo import)
-        uint32_t run[8];
-        {
-            const uint4 t00 = ws.rowv[row];
-            run[0] = t00.x;
-            run[1] = t00.y;
-            run[2] = t00.z;
-            run[3] = run[4] = run[5] = run[6] = run[7] = 0;
-            if (cells) {
-                const uint4 t10 = ws.rowv[row + g.ry], t01 = ws.rowv[row + 1], t11 = ws.rowv[row + g.ry + 1];
-                run[3] = t10.y;
-                run[4] = t10.z;
-                run[5] = t01.x;
-                run[6] = t01.z;
-                run[7] = t11.z;
-            }
-        }
-        unsigned long long frun = ws.rowf[row];
-
-        for (int pc = 0; pc < g.pieces; ++pc) {
-            const int w = pc * kPieceWords + lane;
-            const Piece p = load_piece(r, w, g.wz, lane);
-            const uint32_t zv = zvalid_mask(w, g.rz);
-            uint32_t m[8];
-            m[0] = r.has_x ? (p.a ^ p.b) : 0u;
-            m[1] = r.has_y ? (p.a ^ p.d) : 0u;
-            m[2] = (p.a ^ p.a2) & zv;
-            m[3] = cells ? (p.b ^ p.c) : 0u;
-            m[4] = cells ? ((p.b ^ p.b2) & zv) : 0u;
-            m[5] = cells ? (p.d ^ p.c) : 0u;
-            m[6] = cells ? ((p.d ^ p.d2) & zv) : 0u;
-            m[7] = cells ? ((p.c ^ p.c2) & zv) : 0u;
-            const uint32_t act = active_cells(p, zv, cells);
-
-            // two packed scans (12-bit fields; a field's inclusive sum is <= 1024)
-            const unsigned long long ca = (unsigned long long)__popc(m[0]) | ((unsigned long long)__popc(m[1]) << 12) |
-                                          ((unsigned long long)__popc(m[2]) << 24) | ((unsigned long long)__popc(m[3]) << 36) |
-                                          ((unsigned long long)__popc(m[4]) << 48);
-            const unsigned long long cb = (unsigned long long)__popc(m[5]) | ((unsigned long long)__popc(m[6]) << 12) |
-                                          ((unsigned long long)__popc(m[7]) << 24) | ((unsigned long long)__popc(act) << 36);
-            const unsigned long long ia = warp_incl_scan64(ca, lane), ib = warp_incl_scan64(cb, lane);
-            const unsigned long long ta = __shfl_sync(kFull, ia, 31), tb = __shfl_sync(kFull, ib, 31);
-            const unsigned long long ea = ia - ca, eb = ib - cb;
-
-            __syncwarp();  // the previous piece's readers are done with the scratch
-            sc.words[lane] = make_uint4(p.a, p.b, p.c, p.d);
-            sc.words2[lane] = make_uint4(p.a2, p.b2, p.c2, p.d2);
-            uint32_t first[3], tot[3], ex[3];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const unsigned long long e = q < 5 ? ea : eb, t = q < 5 ? ta : tb;
-                const int sh = 12 * (q < 5 ? q : q - 5);
-                const uint32_t exq = (uint32_t)(e >> sh) & 0xfffu, totq = (uint32_t)(t >> sh) & 0xfffu;
-                sc.rank[q][lane] = make_uint2(m[q], run[q] + exq);
-                if (q < 3) {
-                    first[q] = run[q];
-                    tot[q] = totq;
-                    ex[q] = exq;
-                }
-                run[q] += totq;  // first id of the next piece
-            }
-            const uint32_t ncell = (uint32_t)(tb >> 36) & 0xfffu;
-            const uint32_t cell_ex = (uint32_t)(eb >> 36) & 0xfffu;
-
-            // ---- vertices on the row's own +x / +y / +z edges (gen_vertices_kernel) ----
-            // rounds: as many whole axis groups as fit the 1024-entry list (all three unless the
-            // piece is nearly all crossings)
-            for (int q0 = 0; q0 < 3;) {
-                uint32_t start[3] = {0, 0, 0};
-                uint32_t cnt = 0;
-                int q1 = q0;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (q == q1 && (q == q0 || cnt + tot[q] <= (uint32_t)(kPieceWords * 32))) {
-                        start[q] = cnt;
-                        uint32_t mm = m[q], pos = cnt + ex[q];
-                        while (mm) {
-                            const int i = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            sc.list[pos++] = (uint16_t)((lane << 5) | i | (q << 10));
-                        }
-                        cnt += tot[q];
-                        q1 = q + 1;
-                    }
-                }
-                __syncwarp();
-                for (uint32_t k = lane; k < cnt; k += 32) {
-                    const uint32_t ent = sc.list[k];
-                    const uint32_t ax = ent >> 10;
-                    const int64_t z = (int64_t)pc * (kPieceWords * 32) + (ent & 1023u);
-                    const int64_t stride = ax == 0 ? plane : (ax == 1 ? g.rz : 1);
-                    const float d0 = __ldg(grow + z);
-                    const float d1 = __ldg(grow + z + stride);
-                    // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
-                    const float dt = __fdiv_rn(__fsub_rn(prm.thresh, d0), __fsub_rn(d1, d0));
-                    float px = fx, py = fy, pz = (float)z;
-                    if (ax == 0) px = __fadd_rn(px, dt);
-                    if (ax == 1) py = __fadd_rn(py, dt);
-                    if (ax == 2) pz = __fadd_rn(pz, dt);
-                    const uint32_t id = (ax == 0 ? first[0] - start[0] : (ax == 1 ? first[1] - start[1] : first[2] - start[2])) + k;
-                    // vertices * scale + offset as two separately rounded ops (:298)
-                    float *out = verts + (int64_t)id * 3;
-                    out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
-                    out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
-                    out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
-                }
-                __syncwarp();
-                q0 = q1;
-            }
-
-            // ---- faces of the row's cells, voxel-major, table order inside a cell (gen_faces_kernel) ----
-            if (ncell) {
-                uint32_t mm = act, pos = cell_ex;
-                while (mm) {
-                    const int i = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    sc.list[pos++] = (uint16_t)((lane << 5) | i);
-                }
-                __syncwarp();
-                for (uint32_t k0 = 0; k0 < ncell; k0 += 32) {
-                    // one cell per lane: case, triangle count, and one list entry per triangle
-                    const uint32_t k = k0 + lane;
-                    uint32_t nt = 0, zl = 0;
-                    uint64_t tt = 0;
-                    if (k < ncell) {
-                        zl = sc.list[k];
-                        tt = s_table[cube_case_at(sc.words[zl >> 5], sc.words2[zl >> 5], zl & 31)];
-                        nt = (uint32_t)(tt >> 60);
-                    }
-                    const uint32_t tincl = warp_incl_scan(nt, lane);
-                    const uint32_t btot = __shfl_sync(kFull, tincl, 31);
-                    uint32_t tp = tincl - nt;
-                    for (uint32_t t = 0; t < nt; ++t, tt >>= 12) sc.tri[tp++] = zl | (((uint32_t)tt & 0xfffu) << 10);
-                    __syncwarp();
-                    // one triangle per lane: rank its three edges, 12-byte coalesced stores
-                    for (uint32_t j = lane; j < btot; j += 32) {
-                        const uint32_t ent = sc.tri[j];
-                        const uint32_t wl = (ent >> 5) & 31u, i = ent & 31u;
-                        const uint32_t lt = (1u << i) - 1u;
-                        int32_t *out = faces + (frun + j) * 3ull;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const uint32_t nib = (ent >> (10 + 4 * c)) & 15u;
-                            // crossings strictly below sample z (+dz): for dz = 1 the bit at z counts too; at
-                            // i = 31 that makes the whole word count, i.e. the first id of the next word
-                            const uint2 rk = sc.rank[nib & 7u][wl];
-                            out[c] = prm.vertex_id_base + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
-                        }
-                    }
-                    __syncwarp();
-                    frun += btot;
-                }
-            }
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Strip kernels (lane = row).  A warp owns a strip of 32 consecutive rows y0..y0+31 of one plane x
-// and walks their bit words in z order.  Each lane keeps the running ranks of ITS row in registers,
-// so no warp scans are needed to number crossings; the rows (x,y+1) / (x+1,y+1) a lane's cells
-// touch are simply the next lane's words (one shuffle; lane 31 loads row y0+32 itself).  Sparse
-// work from all 32 rows is pooled in shared memory and processed one item per lane.
-//   k_strip<false>  K2a: per-row counts {nx, ny, nz, nf}
-//   k_strip<true>   K3 : vertices and faces
-// ---------------------------------------------------------------------------------------------
-constexpr int kVRing = 128;   // vertex ring entries (a round adds <= 3 per lane, <= 31 are carried over)
-constexpr int kCellPool = 128;  // a round pools <= 4 cells per lane
-
-struct StripScratch {
-    uint4 words[32];            // per row-lane: {a, b, c, d} of the current word
-    uint4 words2[32];           // the same shifted by one sample
-    uint2 rank[8][32];          // per mask q and row-lane: {crossing mask, id of its first crossing}
-    unsigned long long fbase[32];  // per row-lane: index of the row's next face at the start of this word
-    uint32_t rowtris[32];       // per row-lane: triangles emitted so far for this word
-    uint2 vring[kVRing];        // pooled vertices {id, z<<7 | lane<<2 | axis}
-    uint32_t tri[kTriBatch];    // lane | bit<<5 | three (q|dz<<3) nibbles<<10 | offset in row<<22
-    uint16_t cell[kCellPool];   // lane<<5 | bit
-};
-
-__device__ __forceinline__ void load_group(const uint32_t *row, bool ok, int gw, int wz, bool vec, uint32_t out[4]) {
-    if (ok && vec && gw + 4 <= wz) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(row + gw));
-        out[0] = t.x;
-        out[1] = t.y;
-        out[2] = t.z;
-        out[3] = t.w;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = (ok && gw + j < wz) ? __ldg(row + gw + j) : 0u;
-    }
-}
-
-template <bool EMIT>
-__global__ void __launch_bounds__(256, EMIT ? P3D_STRIP_MINBLOCKS : 4)
-    k_strip(const float *__restrict__ grid, McGeom g, McWorkspace ws, McEmitParams prm, float *__restrict__ verts,
-            int32_t *__restrict__ faces) {
-    __shared__ uint64_t s_table[256];  // EMIT: nibbles (q | dz<<3), nibble 15 = #triangles; else only the counts are used
-    __shared__ StripScratch s_scratch[EMIT ? 8 : 1];
+__global__ void __launch_bounds__(kFaceWarps * 32, 3)
+    k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces) {
+    extern __shared__ __align__(16) unsigned char face_smem[];
+    uint64_t *s_table = reinterpret_cast<uint64_t *>(face_smem);  // per case: up to 15 nibbles (q | dz<<3), nibble 15 = #triangles
+    FaceScratch *s_scratch = reinterpret_cast<FaceScratch *>(face_smem + 256 * sizeof(uint64_t));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < 256; c += blockDim.x) {
@@ -567,329 +422,271 @@ __global__ void __launch_bounds__(256, EMIT ? P3D_STRIP_MINBLOCKS : 4)
         s_table[c] = out;
     }
     __syncthreads();
-    StripScratch &sc = s_scratch[EMIT ? warp : 0];
+    FaceScratch &sc = s_scratch[warp];
 
-    const int wz = g.wz;
-    const bool vec = (wz & 3) == 0;
-    const int64_t plane = g.ry * g.rz;
-    const uint32_t nsy = (uint32_t)((g.ry + 31) / 32);
-    const int64_t nstrips = g.owned_x * (int64_t)nsy;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t np = g.np, bstride = 4 * np, plane_pieces = g.ry * np;
+    const int64_t ngroups = (g.npieces + kFaceGroup - 1) / kFaceGroup;
+    const int64_t nwarps = (int64_t)gridDim.x * kFaceWarps;
 
-    for (int64_t strip = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; strip < nstrips; strip += nwarps) {
-        int64_t x;
-        int64_t y0;
-        if (nstrips <= 0x7fffffffll) {
-            const uint32_t xs = (uint32_t)strip / nsy;
-            x = xs;
-            y0 = (int64_t)((uint32_t)strip - xs * nsy) * 32;
+    for (int64_t grp = (int64_t)blockIdx.x * kFaceWarps + warp; grp < ngroups; grp += nwarps) {
+        const int64_t gi = grp * kFaceGroup + lane;
+        const bool valid = gi < g.npieces;
+        int64_t row, x, y;
+        int p;
+        if (g.npieces <= 0x7fffffffll) {
+            const uint32_t rw = (uint32_t)gi / (uint32_t)np;
+            p = (int)((uint32_t)gi - rw * (uint32_t)np);
+            const uint32_t xx = rw / (uint32_t)g.ry;
+            row = rw, x = xx, y = rw - xx * (uint32_t)g.ry;
         } else {
-            x = strip / nsy;
-            y0 = (strip - x * nsy) * 32;
+            row = gi / np;
+            p = (int)(gi - row * np);
+            x = row / g.ry;
+            y = row - x * g.ry;
         }
-        const int64_t y = y0 + lane;
-        const bool valid = y < g.ry;
-        const bool has_x = x + 1 < g.rx;
-        const bool has_y = valid && (y + 1 < g.ry);
-        const uint32_t hx = (valid && has_x) ? 0xffffffffu : 0u;
-        const uint32_t hy = has_y ? 0xffffffffu : 0u;
-        const uint32_t hc = (has_x && has_y) ? 0xffffffffu : 0u;
-        const int64_t row = x * g.ry + y;
-        const uint32_t *pa = ws.bits + row * wz;
-        const uint32_t *pb = pa + g.ry * (int64_t)wz;
-        const bool halo = (lane == 31) && (y0 + 32 < g.ry);  // lane 31 also loads row y0+32
-
-        // per-row running state
-        uint32_t run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        unsigned long long frun = 0;
-        uint32_t nx = 0, ny = 0, nz = 0, nf = 0;
-        if (EMIT && valid) {
-            const uint4 t00 = ws.rowv[row];
-            run[0] = t00.x;
-            run[1] = t00.y;
-            run[2] = t00.z;
-            if (hc) {
-                const uint4 t10 = ws.rowv[row + g.ry], t01 = ws.rowv[row + 1], t11 = ws.rowv[row + g.ry + 1];
-                run[3] = t10.y;
-                run[4] = t10.z;
-                run[5] = t01.x;
-                run[6] = t01.z;
-                run[7] = t11.z;
-            }
-            frun = ws.rowf[row];
+        const bool hc = valid && (x + 1 < g.rx) && (y + 1 < g.ry);
+        uint4 ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
+        if (hc) {
+            ta = ws.ptab[gi];
+            tb = ws.ptab[gi + plane_pieces];
+            td = ws.ptab[gi + np];
+            tcc = ws.ptab[gi + plane_pieces + np];
         }
-        uint32_t vhead = 0, vcount = 0;  // vertex ring (warp-uniform)
-        const float fx = (float)(prm.x_origin + x);  // static_cast<float>(x), :107
-        const int64_t row0 = x * g.ry + y0;
+        const uint32_t nf = hc ? ta.w : 0u;
+        if (!__any_sync(kFull, nf != 0u)) continue;
 
-        auto flush_vertices = [&](uint32_t n) {  // the first n (<= 32) ring entries, one per lane
-            if ((uint32_t)lane < n) {
-                const uint2 ent = sc.vring[(vhead + lane) & (kVRing - 1)];
-                const uint32_t ax = ent.y & 3u, l = (ent.y >> 2) & 31u;
-                const int64_t z = ent.y >> 7;
-                const float *src = grid + (row0 + l) * g.rz + z;
-                const float d0 = __ldg(src);
-                const float d1 = __ldg(src + (ax == 0 ? plane : (ax == 1 ? g.rz : 1)));
-                // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
-                const float dt = __fdiv_rn(__fsub_rn(prm.thresh, d0), __fsub_rn(d1, d0));
-                float px = fx, py = (float)(y0 + l), pz = (float)z;
-                if (ax == 0) px = __fadd_rn(px, dt);
-                if (ax == 1) py = __fadd_rn(py, dt);
-                if (ax == 2) pz = __fadd_rn(pz, dt);
-                // vertices * scale + offset as two separately rounded ops (:298)
-                float *out = verts + (int64_t)ent.x * 3;
-                out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
-                out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
-                out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
-            }
-            vhead += n;
-            vcount -= n;
-        };
-
-        uint32_t na[4], nb[4], nd[4] = {0, 0, 0, 0}, nc[4] = {0, 0, 0, 0};
-        load_group(pa, valid, 0, wz, vec, na);
-        load_group(pb, valid && has_x, 0, wz, vec, nb);
-        if (lane == 31) {
-            load_group(pa + wz, halo, 0, wz, vec, nd);
-            load_group(pb + wz, halo && has_x, 0, wz, vec, nc);
+        // entries of the next piece of the same rows: the cell at bit 127 reads its z+1 edges there
+        uint4 nxa = make_uint4(__shfl_down_sync(kFull, ta.x, 1), __shfl_down_sync(kFull, ta.y, 1), 0, 0);
+        uint32_t tbn_y = __shfl_down_sync(kFull, tb.y, 1), tdn_x = __shfl_down_sync(kFull, td.x, 1);
+        if (lane == 31 && hc && p + 1 < np) {
+            const uint4 t0 = ws.ptab[gi + 1];
+            nxa.x = t0.x, nxa.y = t0.y;
+            tbn_y = ws.ptab[gi + 1 + plane_pieces].y;
+            tdn_x = ws.ptab[gi + 1 + np].x;
         }
+        unsigned long long fbase = 0;
+        if (lane == 0) fbase = ws.f8[grp * (kFaceGroup / 8)];
+        fbase = __shfl_sync(kFull, fbase, 0);
+        const uint32_t finc = warp_incl_scan(nf, lane);
 
-        for (int gw = 0; gw < wz; gw += 4) {
-            uint32_t a[5], b[5], d[5], c[5];
+        uint32_t actw[4] = {0, 0, 0, 0};
+        uint32_t nact = 0;
+        uint4 last_w = make_uint4(0, 0, 0, 0), last_w2 = last_w;  // corner words of word 3 (patch below)
+        if (nf) {
+            const uint32_t *pa = ws.bits + row * bstride + 4 * p;
+            const uint32_t *pb = pa + g.ry * bstride, *pd = pa + bstride, *pc = pb + bstride;
+            const uint4 a4 = __ldg(reinterpret_cast<const uint4 *>(pa)), b4 = __ldg(reinterpret_cast<const uint4 *>(pb));
+            const uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(pc)), d4 = __ldg(reinterpret_cast<const uint4 *>(pd));
+            const bool more = p + 1 < np;
+            const uint32_t a[5] = {a4.x, a4.y, a4.z, a4.w, more ? __ldg(pa + 4) : 0u};
+            const uint32_t b[5] = {b4.x, b4.y, b4.z, b4.w, more ? __ldg(pb + 4) : 0u};
+            const uint32_t c[5] = {c4.x, c4.y, c4.z, c4.w, more ? __ldg(pc + 4) : 0u};
+            const uint32_t d[5] = {d4.x, d4.y, d4.z, d4.w, more ? __ldg(pd + 4) : 0u};
+            uint32_t run[8] = {ta.x, ta.y, ta.z, tb.y, tb.z, td.x, td.z, tcc.z};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                a[j] = na[j];
-                b[j] = nb[j];
-                d[j] = __shfl_down_sync(kFull, na[j], 1);
-                c[j] = __shfl_down_sync(kFull, nb[j], 1);
-                if (lane == 31) {
-                    d[j] = nd[j];
-                    c[j] = nc[j];
-                }
-            }
-            // prefetch the next group; its first word also closes this group's last word
-            load_group(pa, valid, gw + 4, wz, vec, na);
-            load_group(pb, valid && has_x, gw + 4, wz, vec, nb);
-            if (lane == 31) {
-                load_group(pa + wz, halo, gw + 4, wz, vec, nd);
-                load_group(pb + wz, halo && has_x, gw + 4, wz, vec, nc);
-            }
-            a[4] = na[0];
-            b[4] = nb[0];
-            d[4] = __shfl_down_sync(kFull, na[0], 1);
-            c[4] = __shfl_down_sync(kFull, nb[0], 1);
-            if (lane == 31) {
-                d[4] = nd[0];
-                c[4] = nc[0];
-            }
-
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int w = gw + j;
-                if (w >= wz) break;
-                const uint32_t zv = zvalid_mask(w, g.rz);
-                const uint32_t A = a[j], B = b[j], C = c[j], D = d[j];
-                const uint32_t A2 = __funnelshift_r(A, a[j + 1], 1), B2 = __funnelshift_r(B, b[j + 1], 1);
-                const uint32_t C2 = __funnelshift_r(C, c[j + 1], 1), D2 = __funnelshift_r(D, d[j + 1], 1);
-                uint32_t m[8];
-                m[0] = (A ^ B) & hx;        // :29-33  / :100-111
-                m[1] = (A ^ D) & hy;        // :35-39  / :113-124
-                m[2] = (A ^ A2) & zv;       // :41-45  / :126-137 (rows past ry hold zeros)
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t A = a[w], B = b[w], C = c[w], D = d[w];
+                const uint32_t A2 = __funnelshift_r(A, a[w + 1], 1), B2 = __funnelshift_r(B, b[w + 1], 1);
+                const uint32_t C2 = __funnelshift_r(C, c[w + 1], 1), D2 = __funnelshift_r(D, d[w + 1], 1);
+                const uint32_t zv = low_mask(g.rz - 1 - ((int64_t)p * kTileZ + 32 * w));
+                // pad bits are zero, and a masked-out crossing can only sit above every valid cell of the row,
+                // so the masks need no z-validity here (the ids were assigned with it, k_tile)
+                const uint32_t m[8] = {A ^ B, A ^ D, (A ^ A2) & zv, B ^ C, (B ^ B2) & zv, D ^ C, (D ^ D2) & zv, (C ^ C2) & zv};
                 const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
-                const uint32_t act = (any & ~all) & zv & hc;  // :48 / :154
-                if (!EMIT) {
-                    nx += __popc(m[0]);
-                    ny += __popc(m[1]);
-                    nz += __popc(m[2]);
-                    uint32_t rem = act;
-                    const uint4 w4 = make_uint4(A, B, C, D), w42 = make_uint4(A2, B2, C2, D2);
-                    while (rem) {
-                        const int i = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        nf += (uint32_t)(s_table[cube_case_at(w4, w42, i)] >> 60);
-                    }
-                    continue;
-                }
-                m[3] = (B ^ C) & hc;
-                m[4] = (B ^ B2) & zv & hc;
-                m[5] = (D ^ C) & hc;
-                m[6] = (D ^ D2) & zv & hc;
-                m[7] = (C ^ C2) & zv & hc;
-                if (__any_sync(kFull, (m[0] | m[1] | m[2] | act) != 0u)) {  // else: nothing crosses in these 32x32 samples
-
-                // ---- vertices on the rows' own +x / +y / +z edges (gen_vertices_kernel) ----
-                {
-                    uint32_t r0 = m[0], r1 = m[1], r2 = m[2];
-                    uint32_t i0 = run[0], i1 = run[1], i2 = run[2];
-                    const uint32_t zb = (uint32_t)w << 5;
-                    for (;;) {
-                        const uint32_t have = __popc(r0) + __popc(r1) + __popc(r2);
-                        if (!__any_sync(kFull, have != 0u)) break;
-                        const uint32_t take = have < 3u ? have : 3u;
-                        const uint32_t incl = warp_incl_scan(take, lane);
-                        const uint32_t total = __shfl_sync(kFull, incl, 31);
-                        uint32_t pos = vhead + vcount + incl - take;
-                        for (uint32_t t = 0; t < take; ++t) {
-                            uint32_t id, code;
-                            if (r0) {
-                                const uint32_t i = __ffs(r0) - 1;
-                                r0 &= r0 - 1;
-                                id = i0++;
-                                code = ((zb + i) << 7) | (lane << 2) | 0u;
-                            } else if (r1) {
-                                const uint32_t i = __ffs(r1) - 1;
-                                r1 &= r1 - 1;
-                                id = i1++;
-                                code = ((zb + i) << 7) | (lane << 2) | 1u;
-                            } else {
-                                const uint32_t i = __ffs(r2) - 1;
-                                r2 &= r2 - 1;
-                                id = i2++;
-                                code = ((zb + i) << 7) | (lane << 2) | 2u;
-                            }
-                            sc.vring[(pos++) & (kVRing - 1)] = make_uint2(id, code);
-                        }
-                        vcount += total;
-                        __syncwarp();
-                        while (vcount >= 32u) flush_vertices(32u);
-                        __syncwarp();
-                    }
-                }
-
-                // ---- faces, voxel-major within each row, table order inside a cell (gen_faces_kernel) ----
-                if (__any_sync(kFull, act != 0u)) {
-                    sc.words[lane] = make_uint4(A, B, C, D);
-                    sc.words2[lane] = make_uint4(A2, B2, C2, D2);
+                const uint32_t act = (any & ~all) & zv;  // :154,168-176
+                if (act) {
+                    const int slot = lane * 4 + w;
+                    sc.corner[slot][0] = make_uint4(A, B, C, D);
+                    sc.corner[slot][1] = make_uint4(A2, B2, C2, D2);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) sc.rank[q][lane] = make_uint2(m[q], run[q]);
-                    sc.fbase[lane] = frun;
-                    sc.rowtris[lane] = 0u;
-                    __syncwarp();
-                    uint32_t rem = act;
-                    for (;;) {
-                        const uint32_t have = __popc(rem);
-                        if (!__any_sync(kFull, have != 0u)) break;
-                        const uint32_t take = have < 4u ? have : 4u;
-                        const uint32_t incl = warp_incl_scan(take, lane);
-                        const uint32_t total = __shfl_sync(kFull, incl, 31);
-                        uint32_t pos = incl - take;
-                        for (uint32_t t = 0; t < take; ++t) {
-                            const uint32_t i = __ffs(rem) - 1;
-                            rem &= rem - 1;
-                            sc.cell[pos++] = (uint16_t)((lane << 5) | i);
-                        }
-                        __syncwarp();
-                        for (uint32_t k0 = 0; k0 < total; k0 += 32) {
-                            // one cell per lane: case, triangle count, its offset among the row's triangles
-                            const uint32_t k = k0 + lane;
-                            const bool on = k < total;
-                            uint32_t nt = 0, cl = 32u + lane, bit = 0;
-                            uint64_t tt = 0;
-                            if (on) {
-                                const uint32_t e = sc.cell[k];
-                                cl = e >> 5;
-                                bit = e & 31u;
-                                tt = s_table[cube_case_at(sc.words[cl], sc.words2[cl], bit)];
-                                nt = (uint32_t)(tt >> 60);
-                            }
-                            const uint32_t tincl = warp_incl_scan(nt, lane);
-                            const uint32_t btot = __shfl_sync(kFull, tincl, 31);
-                            const uint32_t texcl = tincl - nt;
-                            const uint32_t peers = __match_any_sync(kFull, cl);   // cells of one row are contiguous
-                            const int head = __ffs(peers) - 1, tail = 31 - __clz(peers);
-                            const uint32_t rel = (on ? sc.rowtris[cl] : 0u) + texcl - __shfl_sync(kFull, texcl, head);
-                            __syncwarp();
-                            if (on && lane == tail) sc.rowtris[cl] = rel + nt;
-                            uint32_t tp = texcl;
-                            for (uint32_t t = 0; t < nt; ++t, tt >>= 12)
-                                sc.tri[tp++] = cl | (bit << 5) | (((uint32_t)tt & 0xfffu) << 10) | ((rel + t) << 22);
-                            __syncwarp();
-                            // one triangle per lane: rank its three edges, 12-byte stores
-                            for (uint32_t jj = lane; jj < btot; jj += 32) {
-                                const uint32_t ent = sc.tri[jj];
-                                const uint32_t tl = ent & 31u, i = (ent >> 5) & 31u;
-                                const uint32_t lt = (1u << i) - 1u;
-                                int32_t *out = faces + (sc.fbase[tl] + (ent >> 22)) * 3ull;
-#pragma unroll
-                                for (int cc = 0; cc < 3; ++cc) {
-                                    const uint32_t nib = (ent >> (10 + 4 * cc)) & 15u;
-                                    // crossings below sample z (+dz): for dz = 1 the bit at z counts too; at i = 31
-                                    // the whole word counts, i.e. the id of the first crossing of the next word
-                                    const uint2 rk = sc.rank[nib & 7u][tl];
-                                    out[cc] = prm.vertex_id_base + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
-                                }
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    frun += sc.rowtris[lane];
-                    __syncwarp();
-                }
+                    for (int q = 0; q < 8; q += 2)
+                        *reinterpret_cast<uint4 *>(&sc.rm[slot][q]) = make_uint4(m[q], run[q], m[q + 1], run[q + 1]);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) run[q] += __popc(m[q]);
+                actw[w] = act;
+                nact += __popc(act);
+                if (w == 3) {
+                    last_w = make_uint4(A, B, C, D);
+                    last_w2 = make_uint4(A2, B2, C2, D2);
+                }
             }
         }
-        if (EMIT) {
+        const uint32_t cincl = warp_incl_scan(nact, lane);
+        const uint32_t ncell = __shfl_sync(kFull, cincl, 31);
+        unsigned long long frun = fbase;
+        __syncwarp();
+
+        for (uint32_t c0 = 0; c0 < ncell; c0 += kCellCap) {
+            {
+                uint32_t pos = cincl - nact - c0;  // wraps below the chunk: filtered by the range test
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    for (uint32_t rem = actw[w]; rem; ++pos) {
+                        const int i = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        if (pos < (uint32_t)kCellCap) sc.cell[pos] = (uint16_t)(((lane * 4 + w) << 5) | i);
+                    }
+            }
             __syncwarp();
-            if (vcount) flush_vertices(vcount);
-            __syncwarp();
-        } else if (valid) {
-            ws.rowv[row] = make_uint4(nx, ny, nz, nf);
+            const uint32_t n = ncell - c0 < (uint32_t)kCellCap ? ncell - c0 : (uint32_t)kCellCap;
+            for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+                // one cell per lane: case, triangle count, and one list entry per triangle
+                const uint32_t k = k0 + lane;
+                uint32_t nt = 0, e = 0;
+                uint64_t tt = 0;
+                if (k < n) {
+                    e = sc.cell[k];
+                    tt = s_table[cube_case_at(sc.corner[e >> 5][0], sc.corner[e >> 5][1], e & 31u)];
+                    nt = (uint32_t)(tt >> 60);
+                }
+                const uint32_t tincl = warp_incl_scan(nt, lane);
+                const uint32_t btot = __shfl_sync(kFull, tincl, 31);
+                uint32_t tp = tincl - nt;
+                for (uint32_t t = 0; t < nt; ++t, tt >>= 12) sc.tri[tp++] = e | (((uint32_t)tt & 0xfffu) << 12);
+                __syncwarp();
+                // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
+                for (uint32_t j = lane; j < btot; j += 32) {
+                    const uint32_t ent = sc.tri[j];
+                    const uint32_t slot = (ent >> 5) & 127u, i = ent & 31u;
+                    const uint32_t lt = (1u << i) - 1u;
+                    int32_t *out = faces + (frun + j) * 3ull;
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const uint32_t nib = (ent >> (12 + 4 * cc)) & 15u;
+                        // crossings strictly below sample z (+dz): for dz = 1 the bit at z counts too; at i = 31
+                        // that makes the whole word count, i.e. the first id of the next word
+                        const uint2 rk = sc.rm[slot][nib & 7u];
+                        out[cc] = vbase + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
+                    }
+                }
+                __syncwarp();
+                frun += btot;
+            }
         }
+
+        // the last cell of a piece (bit 127) has its z+1 x-/y-edges in the NEXT piece, which is numbered by
+        // another tile: overwrite those indices with that piece's table entries (its bit 0 is rank 0)
+        if (actw[3] >> 31) {
+            const uint64_t tt0 = s_table[cube_case_at(last_w, last_w2, 31)];
+            const uint32_t nt = (uint32_t)(tt0 >> 60);
+            uint64_t tt = tt0;
+            int32_t *out = faces + (fbase + finc - nt) * 3ull;
+            for (uint32_t t = 0; t < nt; ++t)
+                for (int cc = 0; cc < 3; ++cc, tt >>= 4) {
+                    const uint32_t nib = (uint32_t)tt & 15u;
+                    if (nib & 8u) {
+                        const uint32_t q = nib & 7u;
+                        out[t * 3 + cc] = vbase + (int32_t)(q == 0 ? nxa.x : (q == 1 ? nxa.y : (q == 3 ? tbn_y : tdn_x)));
+                    }
+                }
+        }
+        __syncwarp();
     }
 }
 
-// Kernel selection (measured on B200, gyroid 1024^3, profiles/r1c_*): counting is faster with the
-// lane = row strip kernel (0.35 ms vs 0.49 ms), emission with the warp-per-row kernel (1.6 ms vs
-// 3.9 ms: the strip variant scatters its 12-byte output stores over 32 rows and its unrolled body
-// misses the instruction cache).  P3D_MC_COUNT / P3D_MC_EMIT = row | strip override for A/B runs.
-static bool pick_strip(const char *var, bool dflt) {
-    const char *e = getenv(var);
-    if (!e || !e[0]) return dflt;
-    return e[0] == 's';
+// ---------------------------------------------------------------------------------------------
+// Host side.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
 }
-static bool use_strip_count() {
-    static const bool v = pick_strip("P3D_MC_COUNT", true);
-    return v;
-}
-static bool use_strip_emit() {
-    static const bool v = pick_strip("P3D_MC_EMIT", false);
+
+thread_local const char *g_tile_error = nullptr;
+
+// P3D_MC_LOADER = generic forces the non-TMA staging path (A/B runs, tests)
+bool force_generic() {
+    static const bool v = [] {
+        const char *e = getenv("P3D_MC_LOADER");
+        return e && e[0] == 'g';
+    }();
     return v;
 }
 
-void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
-    if (g.owned_rows <= 0) return;
-    const int sms = sm_count();
-    {
-        if (use_strip_count()) {
-            const int64_t strips = g.owned_x * ((g.ry + 31) / 32), want = (strips + 7) / 8, cap = (int64_t)sms * 4;
-            k_strip<false><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(nullptr, g, ws, McEmitParams{}, nullptr, nullptr);
+template <bool TMA>
+void launch_tile_kernel(const CUtensorMap &map, const float *grid, const McGeom &g, const McWorkspace &ws,
+                        const McEmitParams &p, float *verts, int64_t vcap, int mode, cudaStream_t s) {
+    static const bool attr = [] {
+        cudaFuncSetAttribute(k_tile<TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
+        return true;
+    }();
+    (void)attr;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
+    k_tile<TMA><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, grid, g, ws, p, verts,
+                                                             (unsigned long long)(vcap > 0 ? vcap : 0), mode);
+}
+
+}  // namespace
+
+const char *tile_pass_error() { return g_tile_error; }
+
+void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
+                      int64_t vertex_capacity, int mode, cudaStream_t s) {
+    g_tile_error = nullptr;
+    if (g.ntiles <= 0) return;
+    if (!verts) vertex_capacity = 0;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    // TMA needs a 16-byte aligned base and 16-byte multiples as row / plane strides
+    bool tma = !force_generic() && (g.rz % 4 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    if (tma) {
+        EncodeTiledFn enc = encode_tiled();
+        if (!enc) {
+            tma = false;
         } else {
-            const int64_t want = (g.owned_rows + 7) / 8, cap = (int64_t)sms * 8;
-            k_row_count<<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(g, ws);
+            const cuuint64_t dims[3] = {(cuuint64_t)g.rz, (cuuint64_t)g.ry, (cuuint64_t)g.rx};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.rz * 4, (cuuint64_t)g.ry * (cuuint64_t)g.rz * 4};
+            const cuuint32_t box[3] = {kBoxZ, kTileY + 1, kTileX + 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(grid), dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                g_tile_error = "cuTensorMapEncodeTiled failed";
+                return;
+            }
         }
     }
-    {
-        const int64_t tiles = (g.owned_rows + kScanTile - 1) / kScanTile, cap = (int64_t)sms * 4;
-        k_row_scan<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, s>>>(g, ws, tiles);
-    }
+    if (tma)
+        launch_tile_kernel<true>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
+    else
+        launch_tile_kernel<false>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
 }
 
-void launch_emit(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
-                 int32_t *faces, cudaStream_t s) {
-    if (g.owned_rows <= 0) return;
-    const int sms = sm_count();
-    if (use_strip_emit()) {
-        const int64_t strips = g.owned_x * ((g.ry + 31) / 32), want = (strips + 7) / 8, cap = (int64_t)sms * P3D_STRIP_MINBLOCKS;
-        k_strip<true><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(grid, g, ws, p, verts, faces);
-        return;
-    }
-    const int64_t want = (g.owned_rows + kRowsPerTile - 1) / kRowsPerTile, cap = (int64_t)sms * P3D_EMIT_MINBLOCKS;
-    k_emit<<<(unsigned)(want < cap ? want : cap), kRowsPerTile * 32, 0, s>>>(grid, g, ws, p, verts, faces);
+void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
+    if (g.nscan <= 0) return;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    k_fscan<<<(unsigned)(g.nscan < cap ? g.nscan : cap), 256, 0, s>>>(g, ws);
 }
 
-// Multi-GPU: install the next shard's first-plane row table as this shard's halo-plane numbering.
+void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s) {
+    if (g.npieces <= 0) return;
+    const int64_t groups = (g.npieces + kFaceGroup - 1) / kFaceGroup;
+    const int64_t want = (groups + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * 3;
+    static const bool attr = [] {
+        cudaFuncSetAttribute(k_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaceSmemBytes);
+        return true;
+    }();
+    (void)attr;
+    k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces);
+}
+
+// Multi-GPU: install the next shard's first-plane table as this shard's halo-plane numbering.
 __global__ void k_import_halo(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, uint32_t delta) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -898,9 +695,9 @@ __global__ void k_import_halo(uint4 *__restrict__ dst, const uint4 *__restrict__
     }
 }
 
-void launch_import_halo(uint4 *halo_rows, const uint32_t *table_in, int64_t ry, uint32_t delta, cudaStream_t s) {
-    k_import_halo<<<(unsigned)((ry + 255) / 256), 256, 0, s>>>(halo_rows, reinterpret_cast<const uint4 *>(table_in), ry,
-                                                             delta);
+void launch_import_halo(uint4 *halo_entries, const uint32_t *table_in, int64_t n, uint32_t delta, cudaStream_t s) {
+    if (n <= 0) return;
+    k_import_halo<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(halo_entries, reinterpret_cast<const uint4 *>(table_in), n, delta);
 }
 
 }  // namespace p3d

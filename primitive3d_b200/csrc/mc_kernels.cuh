@@ -2,60 +2,71 @@
 //
 // Replaces count_vertices_faces_kernel / gen_vertices_kernel / gen_faces_kernel of
 // src/prim3d/Utility/marching_cubes.cu:4-209 (reference) with a design that reads the fp32
-// grid once and carries 1 bit per sample between passes:
+// grid ONCE and carries 1 bit per sample (+ 16 bytes per 128 samples) between two passes:
 //
-//   K1 classify     grid (fp32, streamed once, 128-bit loads) -> inside-bit words, 32 samples
-//                   of one z-row per word.  inside = value > thresh (marching_cubes.cu:25).
-//   K2 count+scan   per (x,y) row: popcounts of the x/y/z crossing masks and the triangle
-//                   counts of the row's cells, all from the bit words; one decoupled
-//                   look-back scan over CTA tiles turns them into absolute offsets in the
-//                   same launch (no CUB/thrust).
-//   K3 emit         per row: recomputes the masks, ranks every crossing edge with
-//                   popc + warp scans, fetches the two fp32 endpoints only for crossing
-//                   edges, interpolates in the reference's fp32 operation order
-//                   (marching_cubes.cu:105-109, :298) and writes faces in voxel-major order.
+//   pass A  k_tile    persistent CTAs walk 8x8x128-sample tiles (+1 halo in x, y, z) that TMA
+//                     (cp.async.bulk.tensor, 2-stage mbarrier ring) stages in shared memory.
+//                     Per tile: inside bits (value > thresh, marching_cubes.cu:25) by ballot,
+//                     crossing masks and triangle counts per 32-sample word, a single-pass
+//                     decoupled look-back over tiles for the tile's first vertex id, then the
+//                     vertices themselves, interpolated from the staged fp32 samples in the
+//                     reference's operation order (marching_cubes.cu:105-109, :298).
+//                     Side products: bit words, one 16-byte table entry per (row, 128-sample
+//                     piece) = first id of its x-/y-/z-edge vertices + its triangle count.
+//           k_fscan   exclusive scan (look-back, no CUB/thrust) of the per-piece triangle
+//                     counts in voxel-major order.
+//   pass B  k_faces   a lane per piece: recomputes crossing masks from the bit words, ranks
+//                     any cube edge as table base + popc(mask below z), and writes faces in
+//                     voxel-major cell order, table order inside a cell (marching_cubes.cu:194-208).
 //
-// Vertex numbering (a free choice: the reference's is atomicAdd-arbitrary): rows in C order;
-// inside row r = (x,y): all x-edge vertices by z, then all y-edge, then all z-edge vertices.
-// The id of the edge (voxel p, axis a) is therefore
-//     rowv[row(p)].{vx|vy|vz} + popc(mask_a(row) below z)
-// which any cell can evaluate for its 12 edges from the bit words of its 2x2 rows plus the
-// 16-byte row-table entries of those rows -- no dense vertex-id volume (the reference's
-// 12 B/voxel vertex_grids, marching_cubes.cu:257-259).
+// Vertex numbering (a free choice: the reference's is atomicAdd-arbitrary): tiles in a fixed
+// order that depends on the grid shape only; inside a tile, (x,y) rows in C order; inside a
+// row's 128-sample piece all x-edge vertices by z, then y-edge, then z-edge vertices.  The id of
+// edge (voxel p, axis a) is therefore  table[row(p)][piece(p)].{vx|vy|vz} + popc(mask_a below z)
+// -- no dense vertex-id volume (the reference's 12 B/voxel vertex_grids, marching_cubes.cu:257-259).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace p3d {
 
-constexpr int kRowsPerTile = 8;          // warps per CTA in K2/K3: one (x,y) row per warp
-constexpr int kPieceWords = 32;          // a warp handles a row in pieces of 32 words = 1024 samples
+constexpr int kTileX = 8, kTileY = 8, kTileZ = 128;  // voxels owned by a tile
+constexpr int kPieceWords = kTileZ / 32;             // bit words per (row, piece)
+constexpr int kBoxZ = kTileZ + 4;                    // staged samples per row: +1 halo, 16-byte multiple
+constexpr int kBoxRows = (kTileX + 1) * (kTileY + 1);
+constexpr int kStageBytes = ((kBoxRows * kBoxZ * 4 + 127) / 128) * 128;
+constexpr int kTileThreads = 256;                    // one thread per owned bit word
+constexpr int kFscanTile = 2048;                     // pieces per scan tile (256 threads x 8)
+constexpr int kFaceGroup = 32;                       // pieces per k_faces warp iteration
 
 struct McGeom {
-    int64_t rx, ry, rz;   // local dims
-    int64_t owned_x;      // planes whose rows this launch owns
-    int32_t wz;           // bit words per row = ceil(rz/32)
-    int32_t pieces;       // ceil(wz/32)
-    int64_t owned_rows;   // owned_x * ry
-    int64_t num_tiles;    // ceil(owned_rows / kRowsPerTile)
+    int64_t rx, ry, rz;   // local dims (rx includes the halo plane, if any)
+    int64_t owned_x;      // planes whose edges / cells this launch owns
+    int32_t np;           // 128-sample pieces per row = ceil(rz / 128)
+    int32_t nxb, nyb;     // tile blocks along x (owned planes) and y
+    int32_t band;         // y-blocks per band of the tile order
+    int64_t ntiles;       // nxb * nyb * np
+    int64_t npieces;      // owned_x * ry * np
+    int64_t nscan;        // ceil(npieces / kFscanTile)
 };
 
 // Workspace header (device).  Zeroed before every count.
 struct McHeader {
-    unsigned long long total_v;    // inclusive totals written by the last tile
+    unsigned long long total_v;
     unsigned long long total_f;
-    unsigned int ticket;           // dynamic tile id for the look-back scan
-    unsigned int ticket_emit;
+    unsigned int ticket;       // dynamic tile id of k_tile
+    unsigned int ticket_scan;  // dynamic tile id of k_fscan
     unsigned int pad[2];
 };
 
 struct McWorkspace {
     McHeader *header;
-    uint32_t *bits;                // [rx*ry][wz]
-    uint4 *rowv;                   // [rx*ry] {vx, vy, vz, nf(low 32)}: first id of the row's x/y/z-edge vertices
-    unsigned long long *rowf;      // [rx*ry] first face of the row's cells
-    unsigned long long *status_v;  // [num_tiles] look-back status words
-    unsigned long long *status_f;  // [num_tiles]
+    unsigned long long *status;    // [ntiles] look-back status words of k_tile (vertex ids)
+    unsigned long long *status_f;  // [nscan]  look-back status words of k_fscan
+    uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: first ids of the piece's x/y/z-edge vertices, #triangles
+    uint32_t *nf;                  // [npieces] triangles per piece (input of k_fscan)
+    unsigned long long *f8;        // [ceil(npieces/8)] index of the first face of pieces 8i..
+    uint32_t *bits;                // [rx*ry][4*np] inside bits, 32 samples per word
 };
 
 struct McEmitParams {
@@ -66,10 +77,13 @@ struct McEmitParams {
     int32_t vertex_id_base;        // added to every face index
 };
 
-void launch_classify(const float *grid, const McGeom &g, float thresh, uint32_t *bits, cudaStream_t s);
-void launch_count_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s);
-void launch_emit(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
-                 float *verts, int32_t *faces, cudaStream_t s);
-void launch_import_halo(uint4 *halo_rows, const uint32_t *table_in, int64_t ry, uint32_t delta, cudaStream_t s);
+// mode 0: full pass (side products + vertices with id < vertex_capacity);
+// mode 1: vertices only, after a completed mode-0 pass on the same workspace.
+void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
+                      int64_t vertex_capacity, int mode, cudaStream_t s);
+void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s);
+void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s);
+void launch_import_halo(uint4 *halo_entries, const uint32_t *table_in, int64_t n, uint32_t delta, cudaStream_t s);
+const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor
 
 }  // namespace p3d

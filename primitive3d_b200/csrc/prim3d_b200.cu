@@ -32,32 +32,44 @@ inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
     if (!d || d->rx < 1 || d->ry < 1 || d->rz < 1) return false;
     if (d->owned_x < 0 || d->owned_x > d->rx || d->rx - d->owned_x > 1) return false;
-    if (d->rz > (int64_t)INT_MAX - 64 || d->rx * d->ry > (int64_t)1 << 40) return false;
+    if (d->rx > (int64_t)INT_MAX - 64 || d->ry > (int64_t)INT_MAX - 64 || d->rz > (int64_t)INT_MAX - 256) return false;
     g->rx = d->rx;
     g->ry = d->ry;
     g->rz = d->rz;
     g->owned_x = d->owned_x;
-    g->wz = (int32_t)((d->rz + 31) / 32);
-    g->pieces = (g->wz + p3d::kPieceWords - 1) / p3d::kPieceWords;
-    g->owned_rows = d->owned_x * d->ry;
-    g->num_tiles = (g->owned_rows + p3d::kRowsPerTile - 1) / p3d::kRowsPerTile;
+    g->np = (int32_t)((d->rz + p3d::kTileZ - 1) / p3d::kTileZ);
+    g->nxb = (int32_t)((d->owned_x + p3d::kTileX - 1) / p3d::kTileX);
+    g->nyb = (int32_t)((d->ry + p3d::kTileY - 1) / p3d::kTileY);
+    // tile order: bands of y-blocks sized so that one x-block of a band is ~16 MB of samples; the halo plane
+    // a block shares with the next x-block is then still in L2 when that block reads it
+    const int64_t column_bytes = (int64_t)p3d::kTileX * p3d::kTileY * 4 * d->rz;
+    int64_t band = ((int64_t)16 << 20) / column_bytes;
+    if (band < 1) band = 1;
+    if (band > g->nyb) band = g->nyb;
+    g->band = (int32_t)band;
+    g->ntiles = (int64_t)g->nxb * g->nyb * g->np;
+    g->npieces = d->owned_x * d->ry * g->np;
+    g->nscan = (g->npieces + p3d::kFscanTile - 1) / p3d::kFscanTile;
+    if (g->ntiles > ((int64_t)1 << 31) || d->rx * d->ry * (int64_t)g->np > ((int64_t)1 << 40)) return false;
     return true;
 }
 
 struct Layout {
-    size_t header, bits, rowv, rowf, status_v, status_f, total;
+    size_t header, status, status_f, zero_end, ptab, nf, f8, bits, total;
 };
 
 Layout make_layout(const p3d::McGeom &g) {
     Layout l;
-    const size_t rows = (size_t)(g.rx * g.ry);
+    const size_t all_pieces = (size_t)(g.rx * g.ry) * (size_t)g.np;
     size_t off = 0;
     l.header = off;   off += align_up(sizeof(p3d::McHeader));
-    l.status_v = off; off += align_up((size_t)g.num_tiles * 8);
-    l.status_f = off; off += align_up((size_t)g.num_tiles * 8);
-    l.rowv = off;     off += align_up(rows * sizeof(uint4));
-    l.rowf = off;     off += align_up(rows * 8);
-    l.bits = off;     off += align_up(rows * (size_t)g.wz * 4);
+    l.status = off;   off += align_up((size_t)g.ntiles * 8);
+    l.status_f = off; off += align_up((size_t)g.nscan * 8);
+    l.zero_end = off;  // everything above is zeroed before a count
+    l.ptab = off;     off += align_up(all_pieces * sizeof(uint4));
+    l.nf = off;       off += align_up((size_t)g.npieces * 4 + 32);
+    l.f8 = off;       off += align_up(((size_t)g.npieces / 8 + 1) * 8);
+    l.bits = off;     off += align_up(all_pieces * 16);
     l.total = off;
     return l;
 }
@@ -66,12 +78,29 @@ p3d::McWorkspace bind(void *base, const Layout &l) {
     char *b = static_cast<char *>(base);
     p3d::McWorkspace ws;
     ws.header = reinterpret_cast<p3d::McHeader *>(b + l.header);
-    ws.status_v = reinterpret_cast<unsigned long long *>(b + l.status_v);
+    ws.status = reinterpret_cast<unsigned long long *>(b + l.status);
     ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
-    ws.rowv = reinterpret_cast<uint4 *>(b + l.rowv);
-    ws.rowf = reinterpret_cast<unsigned long long *>(b + l.rowf);
+    ws.ptab = reinterpret_cast<uint4 *>(b + l.ptab);
+    ws.nf = reinterpret_cast<uint32_t *>(b + l.nf);
+    ws.f8 = reinterpret_cast<unsigned long long *>(b + l.f8);
     ws.bits = reinterpret_cast<uint32_t *>(b + l.bits);
     return ws;
+}
+
+p3d::McEmitParams make_params(const p3d_mc_desc *desc, int64_t vertex_id_base) {
+    p3d::McEmitParams prm;
+    prm.thresh = desc->thresh;
+    // marching_cubes.cu:290-297 -- offset = lower; scale = (upper - lower) / resolution, where the
+    // reference's y term reads upper[2] (not upper[1]); replicated because it is observable.
+    prm.scale[0] = (desc->upper[0] - desc->lower[0]) / static_cast<float>(desc->global_rx);
+    prm.scale[1] = (desc->upper[2] - desc->lower[1]) / static_cast<float>(desc->ry);
+    prm.scale[2] = (desc->upper[2] - desc->lower[2]) / static_cast<float>(desc->rz);
+    prm.offset[0] = desc->lower[0];
+    prm.offset[1] = desc->lower[1];
+    prm.offset[2] = desc->lower[2];
+    prm.x_origin = desc->x_origin;
+    prm.vertex_id_base = static_cast<int32_t>(vertex_id_base);
+    return prm;
 }
 
 // One pinned 16-byte landing pad per host thread for the {V,F} readback.
@@ -103,11 +132,20 @@ size_t p3d_mc_workspace_bytes(const p3d_mc_desc *desc) {
     return make_layout(g).total;
 }
 
+int64_t p3d_mc_plane_table_words(const p3d_mc_desc *desc) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return 0;
+    return g.ry * (int64_t)g.np * 4;
+}
+
 p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace, size_t workspace_bytes,
-                        int64_t *counts_host, void *stream) {
+                        float *vertices, int64_t vertex_capacity, int64_t *counts_host, void *stream) {
     p3d::McGeom g;
     if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_count: invalid descriptor");
     if (!grid || !workspace || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_count: null pointer");
+    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_count: global_rx must be >= 1");
+    if (vertex_capacity < 0 || (vertex_capacity > 0 && !vertices))
+        return fail(P3D_ERR_INVALID, "p3d_mc_count: vertex_capacity without a vertex buffer");
     const Layout l = make_layout(g);
     if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_count: workspace too small");
     if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_count: workspace must be 256-byte aligned");
@@ -115,9 +153,10 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
     const p3d::McWorkspace ws = bind(workspace, l);
 
     // header + both look-back status arrays are contiguous: one memset
-    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.rowv, s));
-    p3d::launch_classify(grid, g, desc->thresh, ws.bits, s);
-    p3d::launch_count_scan(g, ws, s);
+    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
+    p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+    if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_count: ") + p3d::tile_pass_error());
+    p3d::launch_face_scan(g, ws, s);
     P3D_CUDA(cudaGetLastError());
 
     int64_t *pin = pinned_counts();
@@ -131,44 +170,50 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
     return P3D_OK;
 }
 
-p3d_status p3d_mc_emit(const p3d_mc_desc *desc, const float *grid, const void *workspace, float *vertices,
-                       int32_t *faces, int64_t vertex_id_base, void *stream) {
+p3d_status p3d_mc_vertices(const p3d_mc_desc *desc, const float *grid, void *workspace, float *vertices,
+                           int64_t vertex_capacity, void *stream) {
     p3d::McGeom g;
-    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_emit: invalid descriptor");
-    if (!grid || !workspace) return fail(P3D_ERR_INVALID, "p3d_mc_emit: null pointer");
-    if (vertex_id_base < 0 || vertex_id_base > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_emit: vertex_id_base out of int32 range");
-    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_emit: global_rx must be >= 1");
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: invalid descriptor");
+    if (!grid || !workspace || (!vertices && vertex_capacity > 0)) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: null pointer");
+    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: global_rx must be >= 1");
     const Layout l = make_layout(g);
-    const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
-
-    p3d::McEmitParams prm;
-    prm.thresh = desc->thresh;
-    // marching_cubes.cu:290-297 -- offset = lower; scale = (upper - lower) / resolution, where the
-    // reference's y term reads upper[2] (not upper[1]); replicated because it is observable.
-    prm.scale[0] = (desc->upper[0] - desc->lower[0]) / static_cast<float>(desc->global_rx);
-    prm.scale[1] = (desc->upper[2] - desc->lower[1]) / static_cast<float>(desc->ry);
-    prm.scale[2] = (desc->upper[2] - desc->lower[2]) / static_cast<float>(desc->rz);
-    prm.offset[0] = desc->lower[0];
-    prm.offset[1] = desc->lower[1];
-    prm.offset[2] = desc->lower[2];
-    prm.x_origin = desc->x_origin;
-    prm.vertex_id_base = static_cast<int32_t>(vertex_id_base);
-    P3D_CUDA(cudaMemsetAsync(&ws.header->ticket_emit, 0, sizeof(unsigned int), static_cast<cudaStream_t>(stream)));
-    p3d::launch_emit(grid, g, ws, prm, vertices, faces, static_cast<cudaStream_t>(stream));
+    const p3d::McWorkspace ws = bind(workspace, l);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    P3D_CUDA(cudaMemsetAsync(&ws.header->ticket, 0, sizeof(unsigned int), s));
+    p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 1, s);
+    if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_vertices: ") + p3d::tile_pass_error());
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }
 
-p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage, void *stream) {
+p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t *faces, int64_t vertex_id_base,
+                        void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_faces: invalid descriptor");
+    if (!workspace) return fail(P3D_ERR_INVALID, "p3d_mc_faces: null pointer");
+    if (vertex_id_base < 0 || vertex_id_base > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_faces: vertex_id_base out of int32 range");
+    const Layout l = make_layout(g);
+    const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
+    p3d::McEmitParams prm = make_params(desc, vertex_id_base);
+    p3d::launch_faces(g, ws, prm, faces, static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage, float *vertices,
+                              int64_t vertex_capacity, void *stream) {
     p3d::McGeom g;
     if (!make_geom(desc, &g) || !grid || !workspace) return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: invalid argument");
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(workspace, l);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (stage) {
-        case 0: P3D_CUDA(cudaMemsetAsync(workspace, 0, l.rowv, s)); break;
-        case 1: p3d::launch_classify(grid, g, desc->thresh, ws.bits, s); break;
-        case 2: p3d::launch_count_scan(g, ws, s); break;
+        case 0: P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s)); break;
+        case 1:
+            p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+            if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, p3d::tile_pass_error());
+            break;
+        case 2: p3d::launch_face_scan(g, ws, s); break;
         default: return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: stage must be 0, 1 or 2");
     }
     P3D_CUDA(cudaGetLastError());
@@ -180,7 +225,7 @@ p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *worksp
     if (!make_geom(desc, &g) || !workspace || !table_out) return fail(P3D_ERR_INVALID, "p3d_mc_export_first_plane: invalid argument");
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
-    P3D_CUDA(cudaMemcpyAsync(table_out, ws.rowv, (size_t)g.ry * sizeof(uint4), cudaMemcpyDeviceToDevice,
+    P3D_CUDA(cudaMemcpyAsync(table_out, ws.ptab, (size_t)(g.ry * g.np) * sizeof(uint4), cudaMemcpyDeviceToDevice,
                              static_cast<cudaStream_t>(stream)));
     return P3D_OK;
 }
@@ -193,10 +238,22 @@ p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace, co
     if (delta < 0 || delta > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_import_halo_plane: delta out of range");
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(workspace, l);
-    p3d::launch_import_halo(ws.rowv + g.owned_rows, table_in, g.ry, static_cast<uint32_t>(delta),
+    p3d::launch_import_halo(ws.ptab + g.owned_x * g.ry * g.np, table_in, g.ry * g.np, static_cast<uint32_t>(delta),
                             static_cast<cudaStream_t>(stream));
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
+}
+
+int64_t p3d_mc_vertex_capacity_hint(const p3d_mc_desc *desc) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return 0;
+    // a closed surface crosses O(N^2) of the N^3 edges; 1/16 vertex per owned sample covers smooth fields
+    // (gyroid 1024^3: 0.038), capped by the 3-per-sample maximum
+    const int64_t samples = g.owned_x * g.ry * g.rz;
+    int64_t cap = samples / 16 + 4096;
+    if (cap > samples * 3) cap = samples * 3;
+    if (cap > INT32_MAX) cap = INT32_MAX;
+    return cap;
 }
 
 p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn alloc, void *alloc_ctx, float **vertices,
@@ -206,15 +263,24 @@ p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn a
     if (!bytes) return fail(P3D_ERR_INVALID, "p3d_mc_run: invalid descriptor");
     void *ws = alloc(alloc_ctx, bytes);
     if (!ws) return fail(P3D_ERR_CUDA, "p3d_mc_run: workspace allocation failed");
+    const int64_t cap = p3d_mc_vertex_capacity_hint(desc);
+    float *spec = static_cast<float *>(alloc(alloc_ctx, (size_t)(cap > 0 ? cap : 1) * 12));
+    if (!spec) return fail(P3D_ERR_CUDA, "p3d_mc_run: vertex allocation failed");
     int64_t counts[2] = {0, 0};
-    p3d_status st = p3d_mc_count(desc, grid, ws, bytes, counts, stream);
+    p3d_status st = p3d_mc_count(desc, grid, ws, bytes, spec, cap, counts, stream);
     if (st != P3D_OK) return st;
     *num_vertices = counts[0];
     *num_faces = counts[1];
-    *vertices = static_cast<float *>(alloc(alloc_ctx, (size_t)(counts[0] > 0 ? counts[0] : 1) * 12));
+    *vertices = spec;
+    if (counts[0] > cap) {  // the speculative buffer was too small: exact buffer, vertices-only second pass
+        *vertices = static_cast<float *>(alloc(alloc_ctx, (size_t)counts[0] * 12));
+        if (!*vertices) return fail(P3D_ERR_CUDA, "p3d_mc_run: output allocation failed");
+        st = p3d_mc_vertices(desc, grid, ws, *vertices, counts[0], stream);
+        if (st != P3D_OK) return st;
+    }
     *faces = static_cast<int32_t *>(alloc(alloc_ctx, (size_t)(counts[1] > 0 ? counts[1] : 1) * 12));
-    if (!*vertices || !*faces) return fail(P3D_ERR_CUDA, "p3d_mc_run: output allocation failed");
-    return p3d_mc_emit(desc, grid, ws, *vertices, *faces, 0, stream);
+    if (!*faces) return fail(P3D_ERR_CUDA, "p3d_mc_run: output allocation failed");
+    return p3d_mc_faces(desc, ws, *faces, 0, stream);
 }
 
 }  // extern "C"

@@ -6,13 +6,14 @@ admits naturally:
   * tensor dim 0 (the slowest axis of idx = i*(Ry*Rz) + j*Rz + k, marching_cubes.cu:20) is split
     into `world` contiguous plane ranges; rank r holds its planes plus ONE halo plane (the first
     plane of rank r+1), because the cells and +x edges of its last plane read it;
-  * every rank runs the same three kernels on its slab (no data-path collective);
+  * every rank runs the same kernels on its slab (no data-path collective);
   * the only exchange is tiny: an all-gather of {V_r, F_r} (16 bytes per rank) whose exclusive
     prefix gives each rank the global id of its first vertex / face, and an all-gather of each
-    rank's first-plane row table (16 bytes per row of one plane) so the cells next to a slab
-    boundary can name the vertices the next rank owns;
+    rank's first-plane piece table (16 bytes per 128 samples of one plane) so the cells next to
+    a slab boundary can name the vertices the next rank owns;
   * outputs stay sharded: rank r returns its vertices and its faces, the faces holding GLOBAL
-    vertex ids.  Concatenating the shards in rank order gives exactly the single-GPU result.
+    vertex ids.  Concatenating the shards in rank order gives the single-GPU mesh: the same
+    triangles in the same (voxel-major) order, over a vertex array numbered shard by shard.
 """
 import ctypes
 from dataclasses import dataclass
@@ -52,6 +53,16 @@ def gather_counts(V, F, device, group=None):
     return [tuple(r) for r in out.view(world, 2).cpu().tolist()]
 
 
+_last_vertex_count = {}   # slab shape -> V of its last extraction (sizes the speculative vertex buffer)
+
+
+def capacity_for(shape):
+    """Vertex capacity for the counting pass: the previous V of this slab shape plus 1/16, or None (= the
+    library's hint, samples / 16) the first time.  Too small only costs a second vertices-only pass."""
+    v = _last_vertex_count.get(tuple(int(s) for s in shape))
+    return None if v is None else min(v + v // 16 + 4096, 2 ** 31 - 1)
+
+
 @dataclass
 class SlabMesh:
     vertices: torch.Tensor      # float32 [V_r, 3], this rank's vertices
@@ -62,7 +73,7 @@ class SlabMesh:
     num_faces_total: int
 
 
-def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None, group=None):
+def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None, group=None, vertex_capacity=None):
     """Extract this rank's shard.
 
     slab: contiguous float32 CUDA tensor holding planes [x_begin, x_begin + slab.shape[0]) of the
@@ -79,10 +90,15 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
     upper = [float(global_rx), float(ry), float(rz)] if upper is None else upper
     desc = capi.McDesc.make(slab.shape, thresh, lower, upper, owned_x=owned, x_origin=x0, global_rx=global_rx)
 
-    V, F, ws = capi.mc_count(desc, slab)
+    if vertex_capacity is None:
+        vertex_capacity = capacity_for(slab.shape)
+    V, F, ws, vbuf = capi.mc_count(desc, slab, vertex_capacity=vertex_capacity)
+    if len(_last_vertex_count) > 64:
+        _last_vertex_count.clear()
+    _last_vertex_count[tuple(int(s) for s in slab.shape)] = V
+    verts = capi.mc_vertices(desc, slab, ws, V, vbuf)   # local: needs nothing from the other ranks
     if world == 1:
-        verts, faces = capi.mc_emit(desc, slab, ws, V, F, 0)
-        return SlabMesh(verts, faces, 0, 0, V, F)
+        return SlabMesh(verts, capi.mc_faces(desc, ws, F, 0), 0, 0, V, F)
 
     L = capi.lib()
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -91,14 +107,15 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
     if v_tot > 2 ** 31 - 1:
         raise OverflowError("global vertex count exceeds the int32 face-index contract")
 
-    # numbering of the boundary plane: everybody publishes its first-plane row table
-    table = torch.empty((ry, 4), dtype=torch.int32, device=slab.device)
+    # numbering of the boundary plane: everybody publishes the piece table of its first plane
+    words = L.p3d_mc_plane_table_words(ctypes.byref(desc))
+    table = torch.empty(words, dtype=torch.int32, device=slab.device)
     capi.check(L.p3d_mc_export_first_plane(ctypes.byref(desc), ws.data_ptr(), table.data_ptr(), stream))
-    tables = torch.empty(world * ry * 4, dtype=torch.int32, device=slab.device)
-    dist.all_gather_into_tensor(tables, table.view(-1), group=group)
-    tables = tables.view(world, ry, 4)
+    tables = torch.empty(world * words, dtype=torch.int32, device=slab.device)
+    dist.all_gather_into_tensor(tables, table, group=group)
+    tables = tables.view(world, words)
     if rank + 1 < world:
         capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(desc), ws.data_ptr(), tables[rank + 1].data_ptr(), int(V),
                                               stream))
-    verts, faces = capi.mc_emit(desc, slab, ws, V, F, v_off)
+    faces = capi.mc_faces(desc, ws, F, v_off)
     return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)

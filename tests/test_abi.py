@@ -19,7 +19,8 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    for s in ["p3d_mc_workspace_bytes", "p3d_mc_count", "p3d_mc_emit", "p3d_mc_run", "p3d_mc_export_first_plane",
+    for s in ["p3d_mc_workspace_bytes", "p3d_mc_vertex_capacity_hint", "p3d_mc_count", "p3d_mc_vertices", "p3d_mc_faces",
+              "p3d_mc_run", "p3d_mc_plane_table_words", "p3d_mc_export_first_plane",
               "p3d_mc_import_halo_plane", "p3d_mt_classify", "p3d_mt_index", "p3d_mt_emit", "p3d_mt_backward",
               "p3d_last_error", "p3d_abi_version"]:
         assert s in syms
@@ -30,14 +31,20 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/prim3d_b200.h but not exported"
-    assert capi.abi_version() == 1
+    assert capi.abi_version() == 2
 
 
-def test_workspace_size_is_about_one_bit_per_sample():
+def test_workspace_size_is_a_few_bits_per_sample():
     from primitive3d_b200 import capi
     d = capi.McDesc.make((1024, 1024, 1024), 0.0)
     n = capi.mc_workspace_bytes(d)
-    assert 1024 ** 3 // 8 < n < 1024 ** 3 // 8 + 40 * 1024 ** 2   # bits + 24 B/row + scan state
+    # 1 bit per sample + 20 bytes per 128-sample piece + its face prefix + scan state: < 0.30 B/sample
+    # (the reference's vertex_grids alone is 12 B/sample, marching_cubes.cu:257-259)
+    assert 1024 ** 3 // 8 < n < int(0.30 * 1024 ** 3)
+    assert capi.lib().p3d_mc_plane_table_words(ctypes.byref(d)) == 1024 * 8 * 4
+    assert capi.lib().p3d_mc_vertex_capacity_hint(ctypes.byref(d)) == 1024 ** 3 // 16 + 4096
+    tiny = capi.McDesc.make((2, 2, 2), 0.0)
+    assert capi.lib().p3d_mc_vertex_capacity_hint(ctypes.byref(tiny)) == 24
     bad = capi.McDesc.make((0, 4, 4), 0.0)
     assert capi.lib().p3d_mc_workspace_bytes(ctypes.byref(bad)) == 0
 

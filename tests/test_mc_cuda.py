@@ -42,9 +42,13 @@ CASES = {
     "noise33_s1": (lambda: inputs.noise((33, 33, 33), 1), 0.0, None, None),
     "noise65_s2": (lambda: inputs.noise((65, 65, 65), 2), 0.0, None, None),
     "noise64_flat": (lambda: inputs.noise((64, 64, 64), 3), 0.0, None, None),
-    "noise_flat_tail": (lambda: inputs.noise((3, 5, 96), 4), 0.0, None, None),      # flat path + <1024 tail
-    "noise_long_rows": (lambda: inputs.noise((3, 4, 2100), 5), 0.0, None, None),    # rows span 3 pieces
+    "noise_flat_tail": (lambda: inputs.noise((3, 5, 96), 4), 0.0, None, None),      # one partial piece, TMA path
+    "noise_long_rows": (lambda: inputs.noise((3, 4, 2100), 5), 0.0, None, None),    # rows span 17 pieces, TMA path
+    "noise_long_rows_odd": (lambda: inputs.noise((3, 4, 2101), 5), 0.0, None, None),  # same, generic loader
     "noise_long_rows_flat": (lambda: inputs.noise((2, 3, 2048), 6), 0.0, None, None),
+    "noise_piece_edges": (lambda: inputs.noise((10, 11, 257), 15), 0.0, None, None),  # piece boundary at 128, 256
+    "noise_blocks": (lambda: inputs.noise((17, 25, 132), 16), 0.0, None, None),      # partial x/y blocks
+    "noise_dense_tile": (lambda: inputs.noise((9, 9, 384), 17), 0.0, None, None),    # > 2048 vertices per tile
     "noncubic": (lambda: inputs.noise((17, 33, 65), 7), 0.0, None, None),
     "ties": (lambda: inputs.ties((24, 24, 24), 8), 0.0, None, None),
     "nan_inf": (nan_inf_grid, 0.0, None, None),
@@ -124,7 +128,7 @@ def test_deterministic_and_misaligned_input():
     a = run_capi(grid, 0.0, None, None)
     b = run_capi(grid, 0.0, None, None)
     assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
-    # a grid whose base pointer is only 4-byte aligned takes the general classify kernel
+    # a grid whose base pointer is only 4-byte aligned takes the generic (non-TMA) staging path
     from primitive3d_b200 import capi
     buf = torch.empty(grid.size + 1, dtype=torch.float32, device="cuda")
     g = buf[1:].view(grid.shape)
@@ -139,13 +143,62 @@ def test_workspace_reuse_and_errors():
     from primitive3d_b200 import capi
     grid = torch.from_numpy(inputs.noise((20, 20, 20), 3)).cuda()
     desc = capi.McDesc.make(grid.shape, 0.0)
-    V, F, ws = capi.mc_count(desc, grid)
-    V2, F2, _ = capi.mc_count(desc, grid, ws)  # same workspace, second run
+    V, F, ws, _ = capi.mc_count(desc, grid)
+    V2, F2, _, _ = capi.mc_count(desc, grid, ws)  # same workspace, second run
     assert (V, F) == (V2, F2)
     small = torch.empty(16, dtype=torch.uint8, device="cuda")
     with pytest.raises(capi.P3DError) as e:
         capi.mc_count(desc, grid, small)
     assert e.value.status == capi.P3D_ERR_WORKSPACE
+
+
+@pytest.mark.parametrize("name", ["noise33_s0", "gyroid128", "noise_long_rows", "bounds_asym"])
+def test_vertex_capacity_paths_agree(name):
+    """The speculative vertex buffer of the counting pass, a too-small one (vertices-only second pass) and
+    no buffer at all give bit-identical vertices; a partial buffer holds exactly the ids below its capacity."""
+    from primitive3d_b200 import capi
+    make, thresh, lower, upper = CASES[name]
+    g = torch.from_numpy(np.ascontiguousarray(make())).cuda()
+    desc = capi.McDesc.make(g.shape, thresh, lower, upper)
+    V, F, ws, vbuf = capi.mc_count(desc, g, vertex_capacity=None)
+    big = capi.mc_count(desc, g, vertex_capacity=V + 100)
+    assert (big[0], big[1]) == (V, F)
+    want = big[3][:V].clone()
+    faces = capi.mc_faces(desc, big[2], F)
+    half = max(V // 2, 1)
+    V3, F3, ws3, part = capi.mc_count(desc, g, vertex_capacity=half)
+    assert (V3, F3) == (V, F) and part.shape[0] == half
+    assert torch.equal(part.view(torch.int32), want[:half].view(torch.int32))
+    full = capi.mc_vertices(desc, g, ws3, V, part)          # V > capacity: second pass
+    assert full.shape[0] == V and torch.equal(full.view(torch.int32), want.view(torch.int32))
+    assert torch.equal(capi.mc_faces(desc, ws3, F), faces)
+    V4, F4, ws4, none = capi.mc_count(desc, g, vertex_capacity=0)
+    assert (V4, F4) == (V, F) and none.shape[0] == 0
+    assert torch.equal(capi.mc_vertices(desc, g, ws4, V, none).view(torch.int32), want.view(torch.int32))
+    if vbuf.shape[0] >= V:
+        assert torch.equal(vbuf[:V].view(torch.int32), want.view(torch.int32))
+
+
+def test_generic_loader_matches_tma(monkeypatch):
+    """rz % 4 != 0 or a misaligned base take the non-TMA staging path of the tile kernel; same shapes through
+    both loaders must agree (the TMA path needs rz % 4 == 0, so compare on such a grid in a subprocess with
+    P3D_MC_LOADER=generic)."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from oracle import inputs; from primitive3d_b200 import capi;"
+            "g = torch.from_numpy(inputs.noise((19, 21, 260), 5)).cuda();"
+            "v, f = capi.marching_cubes(g, 0.0); torch.cuda.synchronize();"
+            "np.savez(sys.argv[1], v=v.cpu().numpy(), f=f.cpu().numpy())") % (os.path.dirname(HERE), HERE)
+    outs = []
+    for mode in ["tma", "generic"]:
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"p3d_loader_{mode}_{os.getpid()}.npz")
+        env = dict(os.environ, P3D_MC_LOADER=mode)
+        subprocess.check_call([sys.executable, "-c", code, path], env=env)
+        outs.append(np.load(path))
+        os.remove(path)
+    assert np.array_equal(outs[0]["v"].view(np.uint32), outs[1]["v"].view(np.uint32))
+    assert np.array_equal(outs[0]["f"], outs[1]["f"])
 
 
 @pytest.mark.parametrize("n,V,F", [(512, 10111488, 20157724)])
@@ -154,9 +207,9 @@ def test_gyroid_known_counts_large(n, V, F):
     from primitive3d_b200 import capi
     g = torch.from_numpy(inputs.gyroid(n)).cuda()
     desc = capi.McDesc.make(g.shape, 0.0)
-    v, f, ws = capi.mc_count(desc, g)
+    v, f, ws, vbuf = capi.mc_count(desc, g)
     assert (v, f) == (V, F)
-    verts, faces = capi.mc_emit(desc, g, ws, v, f)
+    verts, faces = capi.mc_vertices(desc, g, ws, v, vbuf), capi.mc_faces(desc, ws, f)
     ov, of = mc.marching_cubes(g.cpu().numpy(), 0.0)
     assert_same_mesh(verts.cpu().numpy(), faces.cpu().numpy(), ov, of, ordered_faces=True)
 
@@ -183,9 +236,10 @@ def test_gyroid1024_full_size_properties():
     n = 1024
     g = _gyroid_cuda(n)
     desc = capi.McDesc.make(g.shape, 0.0)
-    V, F, ws = capi.mc_count(desc, g)
+    V, F, ws, vbuf = capi.mc_count(desc, g)
     assert (V, F) == (40621056, 81103132)
-    verts, faces = capi.mc_emit(desc, g, ws, V, F)
+    verts, faces = capi.mc_vertices(desc, g, ws, V, vbuf), capi.mc_faces(desc, ws, F)
+    del vbuf
     assert int(faces.min()) == 0 and int(faces.max()) == V - 1
     used = torch.zeros(V, dtype=torch.bool, device="cuda")
     used[faces.reshape(-1).long()] = True

@@ -3,7 +3,8 @@
 CPU: the host-side logic (plane ranges, count exchange over a real world_size-2 gloo group,
 offsets).  GPU: the shard kernels with halo planes and the first-plane table exchange, run as
 "virtual ranks" one after another on one GPU -- concatenating the shards must reproduce the
-single-GPU result array for array (vertex numbering is row-major, so shard order = global order)."""
+single-GPU mesh: the same triangles in the same voxel-major order (corner coordinates bit-identical)
+and the same vertex multiset (vertex ids are numbered shard by shard, so the arrays are permuted)."""
 import ctypes
 import os
 
@@ -78,10 +79,10 @@ def test_virtual_shards_reproduce_single_gpu_result(shape, world, seed):
         _, xh = slab_with_halo(n, world, r)
         slab = grid[x0:xh].contiguous()
         desc = capi.McDesc.make(slab.shape, 0.1, lower, upper, owned_x=x1 - x0, x_origin=x0, global_rx=n)
-        V, F, ws = capi.mc_count(desc, slab)
-        table = torch.empty((shape[1], 4), dtype=torch.int32, device="cuda")
+        V, F, ws, vbuf = capi.mc_count(desc, slab)
+        table = torch.empty(L.p3d_mc_plane_table_words(ctypes.byref(desc)), dtype=torch.int32, device="cuda")
         capi.check(L.p3d_mc_export_first_plane(ctypes.byref(desc), ws.data_ptr(), table.data_ptr(), stream))
-        shards.append(dict(slab=slab, desc=desc, V=V, F=F, ws=ws, table=table))
+        shards.append(dict(slab=slab, desc=desc, V=V, F=F, ws=ws, table=table, vbuf=vbuf))
     counts = [(s["V"], s["F"]) for s in shards]
     assert sum(c[0] for c in counts) == ref_v.shape[0] and sum(c[1] for c in counts) == ref_f.shape[0]
     vs, fs = [], []
@@ -90,9 +91,9 @@ def test_virtual_shards_reproduce_single_gpu_result(shape, world, seed):
         if r + 1 < world:
             capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(s["desc"]), s["ws"].data_ptr(),
                                                   shards[r + 1]["table"].data_ptr(), s["V"], stream))
-        v, f = capi.mc_emit(s["desc"], s["slab"], s["ws"], s["V"], s["F"], v_off)
-        vs.append(v)
-        fs.append(f)
+        vs.append(capi.mc_vertices(s["desc"], s["slab"], s["ws"], s["V"], s["vbuf"]))
+        fs.append(capi.mc_faces(s["desc"], s["ws"], s["F"], v_off))
     torch.cuda.synchronize()
-    assert torch.equal(torch.cat(vs).view(torch.int32), ref_v.view(torch.int32))
-    assert torch.equal(torch.cat(fs), ref_f)
+    from canonical import assert_same_mesh
+    assert_same_mesh(torch.cat(vs).cpu().numpy(), torch.cat(fs).cpu().numpy(), ref_v.cpu().numpy(), ref_f.cpu().numpy(),
+                     ordered_faces=True)
