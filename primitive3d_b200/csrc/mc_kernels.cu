@@ -57,13 +57,68 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass A: k_tile.
+// First vertex id of a tile: a two-level single-pass scan over tiles (no CUB / thrust).
+//
+// Tiles are grouped into rounds of 256 consecutive ids.  A tile publishes its vertex count in its
+// status word and adds it to its round's accumulator; whichever tile completes a round (the 256th
+// arrival) publishes the exclusive prefix of the NEXT round.  A tile's first id is then
+//     prefix[round] + sum of the status words of the tiles before it in its round
+// -- one batch of <= 8 independent loads per lane, however many tiles are in flight (with ~600
+// resident tiles a classic 32-wide look-back walks ~20 dependent windows).  Every wait is on a tile
+// with a smaller id; ids are handed out in increasing order to running CTAs, so the waits end.
+// The result does not depend on arrival order: numbering is deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRoundTiles = 256;
+constexpr unsigned long long kPublished = 1ull << 63;
+constexpr unsigned long long kRoundSumMask = (1ull << 48) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long *>(p) = v;
+}
+
+// Called by one full warp.  publish = false re-reads a completed scan (vertices-only pass).
+__device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspace &ws, uint32_t tile, uint32_t count,
+                                                                uint32_t ntiles, bool publish, int lane) {
+    const uint32_t k = tile / kRoundTiles, j = tile % kRoundTiles;
+    if (publish && lane == 0) {
+        st_status(ws.status + tile, kPublished | count);
+        const uint32_t left = ntiles - k * kRoundTiles, members = left < kRoundTiles ? left : kRoundTiles;
+        const unsigned long long old = atomicAdd(ws.round_acc + k, (1ull << 48) | count);
+        if ((uint32_t)(old >> 48) == members - 1) {  // this tile completes round k
+            unsigned long long base = kPublished;
+            if (k) do base = ld_status(ws.round_prefix + k); while (!(base & kPublished));
+            st_status(ws.round_prefix + k + 1, base + (old & kRoundSumMask) + count);
+        }
+    }
+    unsigned long long s[kRoundTiles / 32];
+    const unsigned long long *st = ws.status + (tile - j);
+#pragma unroll
+    for (int i = 0; i < (int)kRoundTiles / 32; ++i) s[i] = (uint32_t)(lane + 32 * i) < j ? ld_status(st + lane + 32 * i) : kPublished;
+    unsigned long long acc = 0;
+    if (lane == 0 && k) {
+        do acc = ld_status(ws.round_prefix + k); while (!(acc & kPublished));
+        acc &= ~kPublished;
+    }
+#pragma unroll
+    for (int i = 0; i < (int)kRoundTiles / 32; ++i) {
+        while (!(s[i] & kPublished)) s[i] = ld_status(st + lane + 32 * i);
+        acc += s[i] & ~kPublished;
+    }
+    return warp_sum64(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass A: k_tile.  Four CTAs per SM, each with ONE staged tile: while a CTA waits for its TMA load or
+// for its first vertex id, the other three compute.
 //
 // Shared memory of a CTA:
-//   stage[2]   fp32 samples of a tile: rows (xi, yi) of 0..8 x 0..8, kBoxZ samples each
+//   stage      fp32 samples of a tile: rows (xi, yi) of 0..8 x 0..8, kBoxZ samples each (TMA box)
 //   sbits      [81][8] words: inside bits of every staged row (word 4, bit 0 = the halo sample)
-//   s_piece    [64] vertex count of each owned (row, piece)
-//   s_list     compacted crossing edges of the tile: axis<<13 | row<<7 | z
+//   piece      [64] vertex count of each owned (row, piece)
+//   list       compacted crossing edges of the tile: axis<<13 | row<<7 | z
 // A thread owns bit word (row r = tid>>2, word w = tid&3) of the tile in the count phase.
 // ---------------------------------------------------------------------------------------------
 constexpr int kListCap = 2048;
@@ -75,24 +130,26 @@ struct TileSmem {
     uint32_t piece[kTileX * kTileY];
     uint16_t list[kListCap];
     uint8_t ntri[256];  // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
-    unsigned long long bar[2];
+    unsigned long long bar;
     unsigned long long tile_base;
-    int4 coord[2];      // {x0, y0, piece, -}
-    uint32_t tile[2];
+    int4 coord;         // {x0, y0, piece, tile}
 };
-constexpr int kTileSmemBytes = 2 * kStageBytes + (int)sizeof(TileSmem) + 128;
+constexpr int kTileSmemBytes = kStageBytes + (int)sizeof(TileSmem) + 128;
 
 template <bool TMA>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, 4)
     k_tile(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ grid, McGeom g, McWorkspace ws,
            McEmitParams prm, float *__restrict__ verts, unsigned long long vcap, int mode) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    float *stage0 = reinterpret_cast<float *>(sm);
-    TileSmem &S = *reinterpret_cast<TileSmem *>(sm + 2 * kStageBytes);
+    float *tf = reinterpret_cast<float *>(sm);
+    TileSmem &S = *reinterpret_cast<TileSmem *>(sm + kStageBytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ntiles = (uint32_t)g.ntiles;
+    const int rx = (int)g.rx, ry = (int)g.ry, rz = (int)g.rz, ox = (int)g.owned_x, np = g.np;
+    const float thresh = prm.thresh;
+    const int xg0 = (int)prm.x_origin;  // global index of local plane 0 (< 2^31)
 
     // ntri by staged corner order: bit0 = corner 0 (a, z), bit1 = corner 4 (a, z+1), bit2 = corner 1 (b, z),
     // bit3 = corner 5, bit4 = corner 2 (c, z), bit5 = corner 6, bit6 = corner 3 (d, z), bit7 = corner 7
@@ -103,120 +160,105 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                             ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
         S.ntri[c] = (uint8_t)(c_case_table[cs] >> 60);
     }
-
-    // tile id -> coordinates; tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
-    // band x-block major, then y-block, then piece: the x halo plane of a block is re-read from L2, not HBM
-    auto fetch = [&](int st) {
-        const uint32_t t = atomicAdd(&ws.header->ticket, 1u);
-        S.tile[st] = t;
-        if (t >= ntiles) return;
-        const int64_t per_band = (int64_t)g.nxb * g.band * g.np;
-        const int64_t bi = (int64_t)t / per_band, rem = (int64_t)t - bi * per_band;
-        const int64_t left = g.nyb - bi * g.band, cur = left < g.band ? left : g.band;
-        const int64_t xb = rem / (cur * g.np), rem2 = rem - xb * (cur * g.np);
-        const int64_t yi = rem2 / g.np, p = rem2 - yi * g.np;
-        const int x0 = (int)(xb * kTileX), y0 = (int)((bi * g.band + yi) * kTileY);
-        S.coord[st] = make_int4(x0, y0, (int)p, 0);
-        if (TMA) {
-            const uint32_t bar = smem_u32(&S.bar[st]);
-            mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
-            tma_load_3d(smem_u32(sm + st * kStageBytes), &tmap, bar, (int)p * kTileZ, y0, x0);
-        }
-    };
-
-    if (tid == 0) {
-        if (TMA) {
-            mbar_init(smem_u32(&S.bar[0]), 1);
-            mbar_init(smem_u32(&S.bar[1]), 1);
-            mbar_fence_init();
-        }
-        fetch(0);
-        fetch(1);
+    if (TMA && tid == 0) {
+        mbar_init(smem_u32(&S.bar), 1);
+        mbar_fence_init();
     }
-    __syncthreads();
 
-    const int64_t bstride = 4 * (int64_t)g.np;  // bit words per row
-    const float thresh = prm.thresh;
+    // my word of the tile (count phase): row r = (xi, yi), word w
+    const int r = tid >> 2, w = tid & 3;
+    const int xi = r >> 3, yi = r & 7;
+    const int ra = xi * kRowPitch + yi;
+    const uint32_t *sa = &S.sbits[ra * kSbitsStride + w];
+    const int64_t bstride = 4 * (int64_t)np;  // bit words per row
 
     for (uint32_t it = 0;; ++it) {
-        const int st = it & 1;
-        const uint32_t tile = S.tile[st];
+        // ---- next tile: id -> coordinates, TMA load.  Tiles are ordered band by band (a band = `band` y-blocks
+        // over all x), inside a band x-block major, then y-block, then piece: the x halo plane of a block is
+        // re-read from L2, not HBM ----
+        if (tid == 0) {
+            const uint32_t t = atomicAdd(&ws.header->ticket, 1u);
+            int4 c = make_int4(0, 0, 0, (int)t);
+            if (t < ntiles) {
+                const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
+                const uint32_t bi = t / per_band, rem = t - bi * per_band;
+                const uint32_t left = (uint32_t)g.nyb - bi * (uint32_t)g.band, cur = left < (uint32_t)g.band ? left : (uint32_t)g.band;
+                const uint32_t xb = rem / (cur * np), rem2 = rem - xb * (cur * np);
+                const uint32_t yb = rem2 / np, p = rem2 - yb * np;
+                c.x = (int)(xb * kTileX), c.y = (int)((bi * g.band + yb) * kTileY), c.z = (int)p;
+                if (TMA) {
+                    const uint32_t bar = smem_u32(&S.bar);
+                    mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
+                    tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
+                }
+            }
+            S.coord = c;
+        }
+        __syncthreads();
+        const int4 tc = S.coord;
+        const uint32_t tile = (uint32_t)tc.w;
         if (tile >= ntiles) break;
-        const int4 tc = S.coord[st];
-        const int x0 = tc.x, y0 = tc.y, p = tc.z;
-        const int64_t z0 = (int64_t)p * kTileZ;
-        float *tf = TMA ? reinterpret_cast<float *>(sm + st * kStageBytes) : stage0;
+        const int x0 = tc.x, y0 = tc.y, p = tc.z, z0 = p * kTileZ;
 
         if (TMA) {
-            mbar_wait(smem_u32(&S.bar[st]), (it >> 1) & 1u);
+            mbar_wait(smem_u32(&S.bar), it & 1u);
         } else {
             for (int idx = tid; idx < kBoxRows * kBoxZ; idx += kTileThreads) {
-                const int r = idx / kBoxZ, c = idx - r * kBoxZ;
-                const int xi = r / kRowPitch, yi = r - xi * kRowPitch;
-                const int64_t gx = x0 + xi, gy = y0 + yi, gz = z0 + c;
-                tf[idx] = (gx < g.rx && gy < g.ry && gz < g.rz) ? __ldg(grid + (gx * g.ry + gy) * g.rz + gz) : 0.0f;
+                const int rr = idx / kBoxZ, c = idx - rr * kBoxZ;
+                const int bx = rr / kRowPitch, by = rr - bx * kRowPitch;
+                const int gx = x0 + bx, gy = y0 + by, gz = z0 + c;
+                tf[idx] = (gx < rx && gy < ry && gz < rz) ? __ldg(grid + ((int64_t)gx * ry + gy) * rz + gz) : 0.0f;
             }
             __syncthreads();
         }
 
-        // ---- phase 1: inside bits of the 81 staged rows.  inside = value > thresh (:25,31,37,43,50-57) ----
+        // ---- phase 1: inside bits of the 81 staged rows.  inside = value > thresh (:25,31,37,43,50-57).
+        // Samples outside the grid are staged as 0.0f; their bits take part in no mask that is not cut by a
+        // validity test below, so they need no cleaning here. ----
         {
-            const int64_t nz = g.rz - z0;  // samples of this piece inside the grid (>= 1)
-            const bool ztail = nz < kTileZ;
-            const bool halo_ok = nz > kTileZ;
-            for (int r = warp; r < kBoxRows; r += kTileThreads / 32) {
-                const int xi = r / kRowPitch, yi = r - xi * kRowPitch;
-                const bool rowok = (x0 + xi < g.rx) && (y0 + yi < g.ry);
-                const float *src = tf + r * kBoxZ;
-                const float f0 = src[lane], f1 = src[lane + 32], f2 = src[lane + 64], f3 = src[lane + 96];
-                uint32_t b0 = __ballot_sync(kFull, f0 > thresh), b1 = __ballot_sync(kFull, f1 > thresh);
-                uint32_t b2 = __ballot_sync(kFull, f2 > thresh), b3 = __ballot_sync(kFull, f3 > thresh);
-                if (ztail) {
-                    b0 &= low_mask(nz);
-                    b1 &= low_mask(nz - 32);
-                    b2 &= low_mask(nz - 64);
-                    b3 &= low_mask(nz - 96);
-                }
-                if (!rowok) b0 = b1 = b2 = b3 = 0u;
-                if (lane == 0) {
-                    *reinterpret_cast<uint4 *>(&S.sbits[r * kSbitsStride]) = make_uint4(b0, b1, b2, b3);
-                    S.sbits[r * kSbitsStride + 4] = (rowok && halo_ok && src[kTileZ] > thresh) ? 1u : 0u;
-                }
+            auto row_bits = [&](int row) {
+                const float *src = tf + row * kBoxZ + lane;
+                const float f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
+                const uint32_t b0 = __ballot_sync(kFull, f0 > thresh), b1 = __ballot_sync(kFull, f1 > thresh);
+                const uint32_t b2 = __ballot_sync(kFull, f2 > thresh), b3 = __ballot_sync(kFull, f3 > thresh);
+                if (lane == 0) *reinterpret_cast<uint4 *>(&S.sbits[row * kSbitsStride]) = make_uint4(b0, b1, b2, b3);
+            };
+#pragma unroll
+            for (int bx = 0; bx <= kTileX; ++bx) row_bits(bx * kRowPitch + warp);  // rows (bx, yi = warp)
+            row_bits(warp * kRowPitch + kTileY);                                    // rows (bx = warp, yi = 8)
+            if (warp == 0) row_bits(kTileX * kRowPitch + kTileY);                   // row (8, 8)
+            // the halo sample (z0 + 128) of every staged row: a lane per row
+            if (warp >= 1 && warp <= 3) {
+                const int row = (warp - 1) * 32 + lane;
+                if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
             }
         }
         __syncthreads();
 
         // ---- phase 2: crossing masks and counts of my word ----
-        const int r = tid >> 2, w = tid & 3;
-        const int xi = r >> 3, yi = r & 7;
-        const int ra = xi * kRowPitch + yi;
-        const int64_t x = x0 + xi, y = y0 + yi;
-        const bool inrow = (x < g.rx) && (y < g.ry);
-        const bool own = (x < g.owned_x) && (y < g.ry);
-        const bool hx = own && (x + 1 < g.rx), hy = own && (y + 1 < g.ry), hc = hx && hy;
-        const uint32_t *sa = &S.sbits[ra * kSbitsStride + w];
+        const int x = x0 + xi, y = y0 + yi;
+        const bool own = (x < ox) && (y < ry);
+        const bool hx = own && (x + 1 < rx), hy = own && (y + 1 < ry), hc = hx && hy;
         const uint32_t A = sa[0], An = sa[1];
         const uint32_t B = sa[kRowPitch * kSbitsStride], Bn = sa[kRowPitch * kSbitsStride + 1];
         const uint32_t D = sa[kSbitsStride], Dn = sa[kSbitsStride + 1];
         const uint32_t C = sa[(kRowPitch + 1) * kSbitsStride], Cn = sa[(kRowPitch + 1) * kSbitsStride + 1];
-        const uint32_t A2 = __funnelshift_r(A, An, 1), B2 = __funnelshift_r(B, Bn, 1);
-        const uint32_t C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
-        const uint32_t zv = low_mask(g.rz - 1 - (z0 + 32 * w));
+        const uint32_t A2 = __funnelshift_r(A, An, 1);
+        const uint32_t zv = low_mask(rz - 1 - (z0 + 32 * w));  // samples with z + 1 < rz
         const uint32_t m0 = hx ? (A ^ B) : 0u;            // +x edges, :29-33 / :100-111
         const uint32_t m1 = hy ? (A ^ D) : 0u;            // +y edges, :35-39 / :113-124
         const uint32_t m2 = own ? ((A ^ A2) & zv) : 0u;   // +z edges, :41-45 / :126-137
-        uint32_t act = 0u;                                // cells with mixed corners, :48-66
-        if (hc) {
-            const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
-            act = (any & ~all) & zv;
-        }
         uint32_t nf = 0;
-        for (uint32_t rem = act; rem;) {
-            const int i = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const uint32_t code = (__funnelshift_r(A, An, i) & 3u) | ((__funnelshift_r(B, Bn, i) & 3u) << 2) |
-                                  ((__funnelshift_r(C, Cn, i) & 3u) << 4) | ((__funnelshift_r(D, Dn, i) & 3u) << 6);
-            nf += S.ntri[code];
+        if (hc) {                                         // cells with mixed corners, :48-66
+            const uint32_t B2 = __funnelshift_r(B, Bn, 1), C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
+            const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
+            for (uint32_t rem = (any & ~all) & zv; rem;) {
+                const int i = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t code = (__funnelshift_r(A, An, i) & 3u) | ((__funnelshift_r(B, Bn, i) & 3u) << 2) |
+                                      ((__funnelshift_r(C, Cn, i) & 3u) << 4) | ((__funnelshift_r(D, Dn, i) & 3u) << 6);
+                nf += S.ntri[code];
+            }
         }
         // my (row, piece) = 4 adjacent lanes: packed {nx, ny, nz} (8-bit fields, <= 128 each)
         const uint32_t cnt = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 8) | ((uint32_t)__popc(m2) << 16);
@@ -233,43 +275,38 @@ __global__ void __launch_bounds__(kTileThreads, 2)
         nf += __shfl_xor_sync(kFull, nf, 2);
         if (w == 0) S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
 
+        const int64_t grow = (int64_t)x * ry + y;  // my row of the grid
         if (mode == 0) {
-            if (inrow) ws.bits[(x * g.ry + y) * bstride + 4 * p + w] = A;
-            if (own && w == 0) ws.nf[(x * g.ry + y) * g.np + p] = nf;
+            if (x < rx && y < ry) ws.bits[grow * bstride + 4 * p + w] = A;
+            if (own && w == 0) ws.nf[grow * np + p] = nf;
             // the halo plane of a slab sits one past the last x-block when owned_x is a multiple of 8
-            if (tid < 32 && x0 + kTileX == g.owned_x && g.owned_x < g.rx) {
-                const int hy_ = tid >> 2, hw = tid & 3;
-                if (y0 + hy_ < g.ry)
-                    ws.bits[(g.owned_x * g.ry + y0 + hy_) * bstride + 4 * p + hw] =
-                        S.sbits[(kTileX * kRowPitch + hy_) * kSbitsStride + hw];
-            }
+            if (tid < 32 && x0 + kTileX == ox && ox < rx && y0 + (tid >> 2) < ry)
+                ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * bstride + 4 * p + (tid & 3)] =
+                    S.sbits[(kTileX * kRowPitch + (tid >> 2)) * kSbitsStride + (tid & 3)];
         }
         __syncthreads();
 
         // ---- tile scan (every warp redundantly): first vertex of each (row, piece), relative to the tile ----
         uint32_t vt, pe;
         {
-            const uint32_t v0 = S.piece[2 * lane], v1 = S.piece[2 * lane + 1];
-            const uint32_t s2 = v0 + v1, incl = warp_incl_scan(s2, lane);
+            const uint2 v = *reinterpret_cast<const uint2 *>(&S.piece[2 * lane]);
+            const uint32_t s2 = v.x + v.y, incl = warp_incl_scan(s2, lane);
             vt = __shfl_sync(kFull, incl, 31);
-            const uint32_t e0 = incl - s2, e1 = e0 + v0;
-            const uint32_t g0 = __shfl_sync(kFull, e0, r >> 1), g1 = __shfl_sync(kFull, e1, r >> 1);
-            pe = (r & 1) ? g1 : g0;
+            const uint32_t e0 = incl - s2;
+            const uint32_t g0 = __shfl_sync(kFull, e0, r >> 1), g1 = __shfl_sync(kFull, v.x, r >> 1);
+            pe = g0 + ((r & 1) ? g1 : 0u);
         }
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
         const uint32_t wfirst[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
         const uint32_t wmask[3] = {m0, m1, m2};
 
-        // ---- first vertex id of the tile: decoupled look-back over tiles (warp 0) ----
+        // ---- first vertex id of the tile (warp 0) ----
         if (warp == 0) {
-            unsigned long long tb;
-            if (mode == 0) {
-                tb = lookback(ws.status, (int64_t)tile, (unsigned long long)vt, lane);
-                if (lane == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
-            } else {
-                tb = tile ? (ws.status[tile - 1] & kValueMask) : 0ull;
+            const unsigned long long tb = tile_first_vertex(ws, tile, vt, ntiles, mode == 0, lane);
+            if (lane == 0) {
+                S.tile_base = tb;
+                if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
             }
-            if (lane == 0) S.tile_base = tb;
         }
 
         // ---- vertices: compact the crossing edges, then one edge per thread (gen_vertices_kernel :70-138) ----
@@ -286,8 +323,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             __syncthreads();  // list complete; S.tile_base visible
             const unsigned long long tb = S.tile_base;
             if (c0 == 0 && mode == 0 && own && w == 0)
-                ws.ptab[(x * g.ry + y) * g.np + p] =
-                    make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
+                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
             const uint32_t n = vt - c0 < (uint32_t)kListCap ? vt - c0 : (uint32_t)kListCap;
             for (uint32_t k = tid; k < n && vt > c0; k += kTileThreads) {
                 const unsigned long long id = tb + c0 + k;
@@ -300,9 +336,9 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                 const float d1 = src[ax == 0 ? kRowPitch * kBoxZ : (ax == 1 ? kBoxZ : 1)];
                 // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
                 const float dt = __fdiv_rn(__fsub_rn(thresh, d0), __fsub_rn(d1, d0));
-                float px = (float)(prm.x_origin + x0 + (int)exi);  // static_cast<float>(x), :107
+                float px = (float)(xg0 + x0 + (int)exi);  // static_cast<float>(x), :107
                 float py = (float)(y0 + (int)eyi);
-                float pz = (float)(z0 + ez);
+                float pz = (float)(z0 + (int)ez);
                 if (ax == 0) px = __fadd_rn(px, dt);
                 if (ax == 1) py = __fadd_rn(py, dt);
                 if (ax == 2) pz = __fadd_rn(pz, dt);
@@ -314,8 +350,6 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             }
             __syncthreads();  // the list (next chunk) and the stage (next tile) may be overwritten
         }
-
-        if (tid == 0) fetch(st);
     }
 }
 
@@ -371,80 +405,90 @@ __global__ void __launch_bounds__(256) k_fscan(McGeom g, McWorkspace ws) {
 // ---------------------------------------------------------------------------------------------
 // Pass B: k_faces.  Replaces gen_faces_kernel (:140-209).
 //
-// A warp takes 32 consecutive (row, piece) pairs in voxel-major order; lane l owns the 128 cells of
-// piece l.  It recomputes the eight crossing masks of each of its four words,
+// A warp takes 16 consecutive (row, piece) pairs in voxel-major order; a lane owns 64 cells (half a
+// piece: two bit words).  It recomputes the eight crossing masks of its words,
 //   q0 (x,y) x-edges   q1 (x,y) y-edges   q2 (x,y) z-edges   q3 (x+1,y) y-edges
 //   q4 (x+1,y) z-edges q5 (x,y+1) x-edges q6 (x,y+1) z-edges q7 (x+1,y+1) z-edges
 // carries the id of the first crossing of each mask along the piece (table entry + popcounts), and
 // parks {corner words, masks, first ids} of every word with active cells in shared memory.  The sparse
 // work then runs lane-balanced: one active cell per lane (case, triangle count), one triangle per lane
-// (three ranks, 12-byte store).  Cube edge e -> (q, dz) follows the owner map of :178-192:
-//   e: 0 1 2 3 4 5 6 7 8 9 10 11
-//   q: 0 3 5 1 0 3 5 1 2 4  7  6      dz = 1 for e in 4..7 (the edge sits at sample z+1)
+// (three ranks, 12-byte store).  Cube edge e -> entry n of a word's rank table, following the owner map of
+// :178-192:
+//   e: 0 1 2 3 4  5  6  7 8 9 10 11
+//   n: 0 3 5 1 8 10 11  9 2 4  7  6     n = q for the edges at sample z; n = 8.. for e4..e7, which sit at
+// sample z+1 of masks q0, q3, q5, q1: their entries hold {mask >> 1, first id + (mask & 1)}, so that one
+// formula  id = entry.id + popc(entry.mask & bits below z)  serves all twelve.
 // ---------------------------------------------------------------------------------------------
-constexpr uint64_t kEdgeToMask = (0ull << 0) | (3ull << 3) | (5ull << 6) | (1ull << 9) | (0ull << 12) | (3ull << 15) |
-                                 (5ull << 18) | (1ull << 21) | (2ull << 24) | (4ull << 27) | (7ull << 30) |
-                                 (6ull << 33);
+constexpr uint64_t kEdgeToEntry = (0ull << 0) | (3ull << 4) | (5ull << 8) | (1ull << 12) | (8ull << 16) | (10ull << 20) |
+                                  (11ull << 24) | (9ull << 28) | (2ull << 32) | (4ull << 36) | (7ull << 40) |
+                                  (6ull << 44);
 constexpr int kFaceWarps = 4;
-constexpr int kCellCap = 1024;
-constexpr int kTriBatch = 160;  // triangles of one batch of 32 cells (<= 5 each)
+constexpr int kFacePieces = 16;    // pieces per warp iteration
+constexpr int kFaceSlots = 64;     // bit words per warp iteration
+constexpr int kCellCap = 512;
+constexpr int kTriBatch = 160;     // triangles of one batch of 32 cells (<= 5 each)
+constexpr int kRankStride = 13;    // uint2 per slot: 12 entries + 1 pad (bank spread)
 
 struct FaceScratch {
-    uint4 corner[kFaceGroup * 4][2];  // per word slot: {a, b, c, d} at z and at z+1
-    uint2 rm[kFaceGroup * 4][8];      // per word slot and mask q: {crossing mask, id of its first crossing}
-    uint16_t cell[kCellCap];          // slot<<5 | bit
-    uint32_t tri[kTriBatch];          // slot<<5 | bit | three (q | dz<<3) nibbles << 12
+    uint4 corner[kFaceSlots][2];          // per word slot: {a, b, c, d} and the words that follow them in z
+    uint2 rank[kFaceSlots * kRankStride];  // per word slot and entry n: {mask, id of its first crossing (+ vertex_id_base)}
+    uint16_t cell[kCellCap];              // slot<<5 | bit
+    uint32_t tri[kTriBatch];              // slot<<5 | bit | three entry nibbles << 12
 };
-
 constexpr int kFaceSmemBytes = 256 * (int)sizeof(uint64_t) + kFaceWarps * (int)sizeof(FaceScratch);
 
-// 8-bit cube case of the cell at bit i (corner order of :168-176)
-__device__ __forceinline__ uint32_t cube_case_at(const uint4 &w, const uint4 &w2, int i) {
-    return ((w.x >> i) & 1u) | (((w.y >> i) & 1u) << 1) | (((w.z >> i) & 1u) << 2) | (((w.w >> i) & 1u) << 3) |
-           (((w2.x >> i) & 1u) << 4) | (((w2.y >> i) & 1u) << 5) | (((w2.z >> i) & 1u) << 6) | (((w2.w >> i) & 1u) << 7);
+// the cell's 8 corner bits in the order a0 a1 b0 b1 c0 c1 d0 d1 (x0 = sample z, x1 = sample z+1)
+__device__ __forceinline__ uint32_t corner_code(const uint4 &w, const uint4 &n, int i) {
+    return (__funnelshift_r(w.x, n.x, i) & 3u) | ((__funnelshift_r(w.y, n.y, i) & 3u) << 2) |
+           ((__funnelshift_r(w.z, n.z, i) & 3u) << 4) | ((__funnelshift_r(w.w, n.w, i) & 3u) << 6);
 }
 
-__global__ void __launch_bounds__(kFaceWarps * 32, 3)
+__global__ void __launch_bounds__(kFaceWarps * 32, 5)
     k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces) {
     extern __shared__ __align__(16) unsigned char face_smem[];
-    uint64_t *s_table = reinterpret_cast<uint64_t *>(face_smem);  // per case: up to 15 nibbles (q | dz<<3), nibble 15 = #triangles
+    // per corner code: up to 15 entry nibbles, nibble 15 = #triangles
+    uint64_t *s_table = reinterpret_cast<uint64_t *>(face_smem);
     FaceScratch *s_scratch = reinterpret_cast<FaceScratch *>(face_smem + 256 * sizeof(uint64_t));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < 256; c += blockDim.x) {
-        const uint64_t t = c_case_table[c];
+        // c is a corner code; the case index has corner k in bit k (:168-176)
+        const uint32_t cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
+                            ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
+        const uint64_t t = c_case_table[cs];
         const uint32_t n = (uint32_t)(t >> 60);
         uint64_t out = (uint64_t)n << 60;
         for (uint32_t j = 0; j < 3 * n; ++j) {
             const uint32_t e = (uint32_t)(t >> (4 * j)) & 15u;
-            out |= (((kEdgeToMask >> (3 * e)) & 7ull) | ((e & 12u) == 4u ? 8ull : 0ull)) << (4 * j);
+            out |= ((kEdgeToEntry >> (4 * e)) & 15ull) << (4 * j);
         }
         s_table[c] = out;
     }
     __syncthreads();
     FaceScratch &sc = s_scratch[warp];
 
-    const int64_t np = g.np, bstride = 4 * np, plane_pieces = g.ry * np;
-    const int64_t ngroups = (g.npieces + kFaceGroup - 1) / kFaceGroup;
+    const int np = g.np, ry = (int)g.ry, rx = (int)g.rx, rz = (int)g.rz;
+    const int64_t bstride = 4 * (int64_t)np, plane_pieces = (int64_t)ry * np;
+    const int64_t ngroups = (g.npieces + kFacePieces - 1) / kFacePieces;
     const int64_t nwarps = (int64_t)gridDim.x * kFaceWarps;
+    const int h = lane & 1;  // which half of the piece
 
     for (int64_t grp = (int64_t)blockIdx.x * kFaceWarps + warp; grp < ngroups; grp += nwarps) {
-        const int64_t gi = grp * kFaceGroup + lane;
+        const int64_t gi = grp * kFacePieces + (lane >> 1);
         const bool valid = gi < g.npieces;
-        int64_t row, x, y;
-        int p;
+        int64_t row;
+        int p, x, y;
         if (g.npieces <= 0x7fffffffll) {
             const uint32_t rw = (uint32_t)gi / (uint32_t)np;
             p = (int)((uint32_t)gi - rw * (uint32_t)np);
-            const uint32_t xx = rw / (uint32_t)g.ry;
-            row = rw, x = xx, y = rw - xx * (uint32_t)g.ry;
+            x = (int)(rw / (uint32_t)ry), y = (int)(rw - (uint32_t)x * (uint32_t)ry);
+            row = rw;
         } else {
             row = gi / np;
             p = (int)(gi - row * np);
-            x = row / g.ry;
-            y = row - x * g.ry;
+            x = (int)(row / ry), y = (int)(row - (int64_t)x * ry);
         }
-        const bool hc = valid && (x + 1 < g.rx) && (y + 1 < g.ry);
+        const bool hc = valid && (x + 1 < rx) && (y + 1 < ry);
         uint4 ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
         if (hc) {
             ta = ws.ptab[gi];
@@ -456,60 +500,84 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 3)
         if (!__any_sync(kFull, nf != 0u)) continue;
 
         // entries of the next piece of the same rows: the cell at bit 127 reads its z+1 edges there
-        uint4 nxa = make_uint4(__shfl_down_sync(kFull, ta.x, 1), __shfl_down_sync(kFull, ta.y, 1), 0, 0);
-        uint32_t tbn_y = __shfl_down_sync(kFull, tb.y, 1), tdn_x = __shfl_down_sync(kFull, td.x, 1);
-        if (lane == 31 && hc && p + 1 < np) {
+        uint32_t nax = __shfl_down_sync(kFull, ta.x, 2), nay = __shfl_down_sync(kFull, ta.y, 2);
+        uint32_t nby = __shfl_down_sync(kFull, tb.y, 2), ndx = __shfl_down_sync(kFull, td.x, 2);
+        if (lane >= 30 && hc && p + 1 < np) {
             const uint4 t0 = ws.ptab[gi + 1];
-            nxa.x = t0.x, nxa.y = t0.y;
-            tbn_y = ws.ptab[gi + 1 + plane_pieces].y;
-            tdn_x = ws.ptab[gi + 1 + np].x;
+            nax = t0.x, nay = t0.y;
+            nby = ws.ptab[gi + 1 + plane_pieces].y;
+            ndx = ws.ptab[gi + 1 + np].x;
         }
         unsigned long long fbase = 0;
-        if (lane == 0) fbase = ws.f8[grp * (kFaceGroup / 8)];
+        if (lane == 0) fbase = ws.f8[grp * (kFacePieces / 8)];
         fbase = __shfl_sync(kFull, fbase, 0);
-        const uint32_t finc = warp_incl_scan(nf, lane);
+        const uint32_t finc = warp_incl_scan(h ? 0u : nf, lane);  // faces of the pieces up to and including mine
 
-        uint32_t actw[4] = {0, 0, 0, 0};
+        uint32_t actw[2] = {0, 0};
         uint32_t nact = 0;
-        uint4 last_w = make_uint4(0, 0, 0, 0), last_w2 = last_w;  // corner words of word 3 (patch below)
-        if (nf) {
-            const uint32_t *pa = ws.bits + row * bstride + 4 * p;
-            const uint32_t *pb = pa + g.ry * bstride, *pd = pa + bstride, *pc = pb + bstride;
-            const uint4 a4 = __ldg(reinterpret_cast<const uint4 *>(pa)), b4 = __ldg(reinterpret_cast<const uint4 *>(pb));
-            const uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(pc)), d4 = __ldg(reinterpret_cast<const uint4 *>(pd));
-            const bool more = p + 1 < np;
-            const uint32_t a[5] = {a4.x, a4.y, a4.z, a4.w, more ? __ldg(pa + 4) : 0u};
-            const uint32_t b[5] = {b4.x, b4.y, b4.z, b4.w, more ? __ldg(pb + 4) : 0u};
-            const uint32_t c[5] = {c4.x, c4.y, c4.z, c4.w, more ? __ldg(pc + 4) : 0u};
-            const uint32_t d[5] = {d4.x, d4.y, d4.z, d4.w, more ? __ldg(pd + 4) : 0u};
+        uint4 last_w = make_uint4(0, 0, 0, 0), last_n = last_w;  // corner words of the piece's last word (patch below)
+        {
+            uint32_t m[2][8];
+            uint32_t A[3] = {0, 0, 0}, B[3] = {0, 0, 0}, C[3] = {0, 0, 0}, D[3] = {0, 0, 0};
+            if (nf) {
+                const uint32_t *pa = ws.bits + row * bstride + 4 * p + 2 * h;
+                const uint32_t *pb = pa + ry * bstride, *pd = pa + bstride, *pc = pb + bstride;
+                const uint2 a2 = __ldg(reinterpret_cast<const uint2 *>(pa)), b2 = __ldg(reinterpret_cast<const uint2 *>(pb));
+                const uint2 c2 = __ldg(reinterpret_cast<const uint2 *>(pc)), d2 = __ldg(reinterpret_cast<const uint2 *>(pd));
+                const bool more = h == 0 || p + 1 < np;  // the word after mine exists in the row
+                A[0] = a2.x, A[1] = a2.y, A[2] = more ? __ldg(pa + 2) : 0u;
+                B[0] = b2.x, B[1] = b2.y, B[2] = more ? __ldg(pb + 2) : 0u;
+                C[0] = c2.x, C[1] = c2.y, C[2] = more ? __ldg(pc + 2) : 0u;
+                D[0] = d2.x, D[1] = d2.y, D[2] = more ? __ldg(pd + 2) : 0u;
+            }
+            uint32_t half_lo = 0, half_hi = 0;  // crossings of my two words per mask, 8-bit fields
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t A2 = __funnelshift_r(A[w], A[w + 1], 1), B2 = __funnelshift_r(B[w], B[w + 1], 1);
+                const uint32_t C2 = __funnelshift_r(C[w], C[w + 1], 1), D2 = __funnelshift_r(D[w], D[w + 1], 1);
+                const uint32_t zv = low_mask(rz - 1 - (p * kTileZ + 32 * (2 * h + w)));
+                // samples outside the grid were staged as 0.0f in every row, so the x/y masks are zero there, and a
+                // z crossing cut by zv can only sit above every valid cell of the row
+                m[w][0] = A[w] ^ B[w], m[w][1] = A[w] ^ D[w], m[w][2] = (A[w] ^ A2) & zv, m[w][3] = B[w] ^ C[w];
+                m[w][4] = (B[w] ^ B2) & zv, m[w][5] = D[w] ^ C[w], m[w][6] = (D[w] ^ D2) & zv, m[w][7] = (C[w] ^ C2) & zv;
+                const uint32_t any = A[w] | B[w] | C[w] | D[w] | A2 | B2 | C2 | D2;
+                const uint32_t all = A[w] & B[w] & C[w] & D[w] & A2 & B2 & C2 & D2;
+                actw[w] = nf ? ((any & ~all) & zv) : 0u;  // :154,168-176
+                nact += __popc(actw[w]);
+                half_lo += (uint32_t)__popc(m[w][0]) | ((uint32_t)__popc(m[w][1]) << 8) | ((uint32_t)__popc(m[w][2]) << 16) |
+                           ((uint32_t)__popc(m[w][3]) << 24);
+                half_hi += (uint32_t)__popc(m[w][4]) | ((uint32_t)__popc(m[w][5]) << 8) | ((uint32_t)__popc(m[w][6]) << 16) |
+                           ((uint32_t)__popc(m[w][7]) << 24);
+            }
+            // first ids at my first word: the table entry, plus the first half's crossings for the second half
+            const uint32_t prev_lo = __shfl_up_sync(kFull, half_lo, 1), prev_hi = __shfl_up_sync(kFull, half_hi, 1);
             uint32_t run[8] = {ta.x, ta.y, ta.z, tb.y, tb.z, td.x, td.z, tcc.z};
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const uint32_t A = a[w], B = b[w], C = c[w], D = d[w];
-                const uint32_t A2 = __funnelshift_r(A, a[w + 1], 1), B2 = __funnelshift_r(B, b[w + 1], 1);
-                const uint32_t C2 = __funnelshift_r(C, c[w + 1], 1), D2 = __funnelshift_r(D, d[w + 1], 1);
-                const uint32_t zv = low_mask(g.rz - 1 - ((int64_t)p * kTileZ + 32 * w));
-                // pad bits are zero, and a masked-out crossing can only sit above every valid cell of the row,
-                // so the masks need no z-validity here (the ids were assigned with it, k_tile)
-                const uint32_t m[8] = {A ^ B, A ^ D, (A ^ A2) & zv, B ^ C, (B ^ B2) & zv, D ^ C, (D ^ D2) & zv, (C ^ C2) & zv};
-                const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
-                const uint32_t act = (any & ~all) & zv;  // :154,168-176
-                if (act) {
-                    const int slot = lane * 4 + w;
-                    sc.corner[slot][0] = make_uint4(A, B, C, D);
-                    sc.corner[slot][1] = make_uint4(A2, B2, C2, D2);
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t prev = ((q < 4 ? prev_lo : prev_hi) >> (8 * (q & 3))) & 255u;
+                run[q] += (uint32_t)vbase + (h ? prev : 0u);
+            }
 #pragma unroll
-                    for (int q = 0; q < 8; q += 2)
-                        *reinterpret_cast<uint4 *>(&sc.rm[slot][q]) = make_uint4(m[q], run[q], m[q + 1], run[q + 1]);
+            for (int w = 0; w < 2; ++w) {
+                if (actw[w]) {
+                    const int slot = lane * 2 + w;
+                    sc.corner[slot][0] = make_uint4(A[w], B[w], C[w], D[w]);
+                    sc.corner[slot][1] = make_uint4(A[w + 1], B[w + 1], C[w + 1], D[w + 1]);
+                    uint2 *rk = &sc.rank[slot * kRankStride];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) rk[q] = make_uint2(m[w][q], run[q]);
+                    // e4..e7: the crossing at sample z+1 of masks q0, q1, q3, q5
+                    rk[8] = make_uint2(m[w][0] >> 1, run[0] + (m[w][0] & 1u));
+                    rk[9] = make_uint2(m[w][1] >> 1, run[1] + (m[w][1] & 1u));
+                    rk[10] = make_uint2(m[w][3] >> 1, run[3] + (m[w][3] & 1u));
+                    rk[11] = make_uint2(m[w][5] >> 1, run[5] + (m[w][5] & 1u));
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) run[q] += __popc(m[q]);
-                actw[w] = act;
-                nact += __popc(act);
-                if (w == 3) {
-                    last_w = make_uint4(A, B, C, D);
-                    last_w2 = make_uint4(A2, B2, C2, D2);
-                }
+                for (int q = 0; q < 8; ++q) run[q] += __popc(m[w][q]);
+            }
+            if (h) {
+                last_w = make_uint4(A[1], B[1], C[1], D[1]);
+                last_n = make_uint4(A[2], B[2], C[2], D[2]);
             }
         }
         const uint32_t cincl = warp_incl_scan(nact, lane);
@@ -521,11 +589,11 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 3)
             {
                 uint32_t pos = cincl - nact - c0;  // wraps below the chunk: filtered by the range test
 #pragma unroll
-                for (int w = 0; w < 4; ++w)
+                for (int w = 0; w < 2; ++w)
                     for (uint32_t rem = actw[w]; rem; ++pos) {
                         const int i = __ffs(rem) - 1;
                         rem &= rem - 1;
-                        if (pos < (uint32_t)kCellCap) sc.cell[pos] = (uint16_t)(((lane * 4 + w) << 5) | i);
+                        if (pos < (uint32_t)kCellCap) sc.cell[pos] = (uint16_t)(((lane * 2 + w) << 5) | i);
                     }
             }
             __syncwarp();
@@ -537,27 +605,30 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 3)
                 uint64_t tt = 0;
                 if (k < n) {
                     e = sc.cell[k];
-                    tt = s_table[cube_case_at(sc.corner[e >> 5][0], sc.corner[e >> 5][1], e & 31u)];
+                    tt = s_table[corner_code(sc.corner[e >> 5][0], sc.corner[e >> 5][1], e & 31u)];
                     nt = (uint32_t)(tt >> 60);
                 }
                 const uint32_t tincl = warp_incl_scan(nt, lane);
                 const uint32_t btot = __shfl_sync(kFull, tincl, 31);
                 uint32_t tp = tincl - nt;
-                for (uint32_t t = 0; t < nt; ++t, tt >>= 12) sc.tri[tp++] = e | (((uint32_t)tt & 0xfffu) << 12);
+                uint32_t lo = (uint32_t)tt, hi = (uint32_t)(tt >> 32);
+                for (uint32_t t = 0; t < nt; ++t) {
+                    sc.tri[tp++] = e | ((lo & 0xfffu) << 12);
+                    lo = __funnelshift_r(lo, hi, 12);
+                    hi >>= 12;
+                }
                 __syncwarp();
                 // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
                 for (uint32_t j = lane; j < btot; j += 32) {
                     const uint32_t ent = sc.tri[j];
-                    const uint32_t slot = (ent >> 5) & 127u, i = ent & 31u;
+                    const uint32_t i = ent & 31u;
                     const uint32_t lt = (1u << i) - 1u;
+                    const uint2 *rk = &sc.rank[((ent >> 5) & 63u) * kRankStride];
                     int32_t *out = faces + (frun + j) * 3ull;
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
-                        const uint32_t nib = (ent >> (12 + 4 * cc)) & 15u;
-                        // crossings strictly below sample z (+dz): for dz = 1 the bit at z counts too; at i = 31
-                        // that makes the whole word count, i.e. the first id of the next word
-                        const uint2 rk = sc.rm[slot][nib & 7u];
-                        out[cc] = vbase + (int32_t)(rk.y + __popc(rk.x & (lt | ((nib >> 3) << i))));
+                        const uint2 en = rk[(ent >> (12 + 4 * cc)) & 15u];
+                        out[cc] = (int32_t)(en.y + __popc(en.x & lt));  // crossings of the mask below the edge's sample
                     }
                 }
                 __syncwarp();
@@ -567,18 +638,14 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 3)
 
         // the last cell of a piece (bit 127) has its z+1 x-/y-edges in the NEXT piece, which is numbered by
         // another tile: overwrite those indices with that piece's table entries (its bit 0 is rank 0)
-        if (actw[3] >> 31) {
-            const uint64_t tt0 = s_table[cube_case_at(last_w, last_w2, 31)];
-            const uint32_t nt = (uint32_t)(tt0 >> 60);
-            uint64_t tt = tt0;
+        if (h && (actw[1] >> 31)) {
+            uint64_t tt = s_table[corner_code(last_w, last_n, 31)];
+            const uint32_t nt = (uint32_t)(tt >> 60);
             int32_t *out = faces + (fbase + finc - nt) * 3ull;
             for (uint32_t t = 0; t < nt; ++t)
                 for (int cc = 0; cc < 3; ++cc, tt >>= 4) {
-                    const uint32_t nib = (uint32_t)tt & 15u;
-                    if (nib & 8u) {
-                        const uint32_t q = nib & 7u;
-                        out[t * 3 + cc] = vbase + (int32_t)(q == 0 ? nxa.x : (q == 1 ? nxa.y : (q == 3 ? tbn_y : tdn_x)));
-                    }
+                    const uint32_t n = (uint32_t)tt & 15u;
+                    if (n >= 8u) out[t * 3 + cc] = vbase + (int32_t)(n == 8u ? nax : (n == 9u ? nay : (n == 10u ? nby : ndx)));
                 }
         }
         __syncwarp();
@@ -625,7 +692,7 @@ void launch_tile_kernel(const CUtensorMap &map, const float *grid, const McGeom 
         return true;
     }();
     (void)attr;
-    const int64_t cap = (int64_t)sm_count() * 2;
+    const int64_t cap = (int64_t)sm_count() * 4;
     const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
     k_tile<TMA><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, grid, g, ws, p, verts,
                                                              (unsigned long long)(vcap > 0 ? vcap : 0), mode);
@@ -676,8 +743,8 @@ void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
 
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s) {
     if (g.npieces <= 0) return;
-    const int64_t groups = (g.npieces + kFaceGroup - 1) / kFaceGroup;
-    const int64_t want = (groups + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * 3;
+    const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
+    const int64_t want = (groups + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * 5;
     static const bool attr = [] {
         cudaFuncSetAttribute(k_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaceSmemBytes);
         return true;

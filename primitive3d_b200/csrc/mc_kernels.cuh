@@ -37,7 +37,6 @@ constexpr int kBoxRows = (kTileX + 1) * (kTileY + 1);
 constexpr int kStageBytes = ((kBoxRows * kBoxZ * 4 + 127) / 128) * 128;
 constexpr int kTileThreads = 256;                    // one thread per owned bit word
 constexpr int kFscanTile = 2048;                     // pieces per scan tile (256 threads x 8)
-constexpr int kFaceGroup = 32;                       // pieces per k_faces warp iteration
 
 struct McGeom {
     int64_t rx, ry, rz;   // local dims (rx includes the halo plane, if any)
@@ -48,6 +47,7 @@ struct McGeom {
     int64_t ntiles;       // nxb * nyb * np
     int64_t npieces;      // owned_x * ry * np
     int64_t nscan;        // ceil(npieces / kFscanTile)
+    int64_t nrounds;      // ceil(ntiles / 256): rounds of the tile scan
 };
 
 // Workspace header (device).  Zeroed before every count.
@@ -61,7 +61,9 @@ struct McHeader {
 
 struct McWorkspace {
     McHeader *header;
-    unsigned long long *status;    // [ntiles] look-back status words of k_tile (vertex ids)
+    unsigned long long *status;    // [ntiles] published vertex count of each tile (k_tile)
+    unsigned long long *round_acc;     // [nrounds] arrivals<<48 | vertex count of each round of 256 tiles
+    unsigned long long *round_prefix;  // [nrounds + 1] published exclusive vertex prefix of each round
     unsigned long long *status_f;  // [nscan]  look-back status words of k_fscan
     uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: first ids of the piece's x/y/z-edge vertices, #triangles
     uint32_t *nf;                  // [npieces] triangles per piece (input of k_fscan)

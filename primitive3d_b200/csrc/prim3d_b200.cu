@@ -50,12 +50,13 @@ bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
     g->ntiles = (int64_t)g->nxb * g->nyb * g->np;
     g->npieces = d->owned_x * d->ry * g->np;
     g->nscan = (g->npieces + p3d::kFscanTile - 1) / p3d::kFscanTile;
+    g->nrounds = (g->ntiles + 255) / 256;
     if (g->ntiles > ((int64_t)1 << 31) || d->rx * d->ry * (int64_t)g->np > ((int64_t)1 << 40)) return false;
     return true;
 }
 
 struct Layout {
-    size_t header, status, status_f, zero_end, ptab, nf, f8, bits, total;
+    size_t header, status, round_acc, round_prefix, status_f, zero_end, ptab, nf, f8, bits, total;
 };
 
 Layout make_layout(const p3d::McGeom &g) {
@@ -64,6 +65,8 @@ Layout make_layout(const p3d::McGeom &g) {
     size_t off = 0;
     l.header = off;   off += align_up(sizeof(p3d::McHeader));
     l.status = off;   off += align_up((size_t)g.ntiles * 8);
+    l.round_acc = off;    off += align_up((size_t)g.nrounds * 8);
+    l.round_prefix = off; off += align_up((size_t)(g.nrounds + 1) * 8);
     l.status_f = off; off += align_up((size_t)g.nscan * 8);
     l.zero_end = off;  // everything above is zeroed before a count
     l.ptab = off;     off += align_up(all_pieces * sizeof(uint4));
@@ -79,6 +82,8 @@ p3d::McWorkspace bind(void *base, const Layout &l) {
     p3d::McWorkspace ws;
     ws.header = reinterpret_cast<p3d::McHeader *>(b + l.header);
     ws.status = reinterpret_cast<unsigned long long *>(b + l.status);
+    ws.round_acc = reinterpret_cast<unsigned long long *>(b + l.round_acc);
+    ws.round_prefix = reinterpret_cast<unsigned long long *>(b + l.round_prefix);
     ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
     ws.ptab = reinterpret_cast<uint4 *>(b + l.ptab);
     ws.nf = reinterpret_cast<uint32_t *>(b + l.nf);
