@@ -79,20 +79,23 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
 
-// Called by one full warp.  publish = false re-reads a completed scan (vertices-only pass).
-__device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspace &ws, uint32_t tile, uint32_t count,
-                                                                uint32_t ntiles, bool publish, int lane) {
-    const uint32_t k = tile / kRoundTiles, j = tile % kRoundTiles;
-    if (publish && lane == 0) {
-        st_status(ws.status + tile, kPublished | count);
-        const uint32_t left = ntiles - k * kRoundTiles, members = left < kRoundTiles ? left : kRoundTiles;
-        const unsigned long long old = atomicAdd(ws.round_acc + k, (1ull << 48) | count);
-        if ((uint32_t)(old >> 48) == members - 1) {  // this tile completes round k
-            unsigned long long base = kPublished;
-            if (k) do base = ld_status(ws.round_prefix + k); while (!(base & kPublished));
-            st_status(ws.round_prefix + k + 1, base + (old & kRoundSumMask) + count);
-        }
+// Lane 0 of the warp that owns `tile`: publish its vertex count.
+__device__ __forceinline__ void tile_publish(const McWorkspace &ws, uint32_t tile, uint32_t count, uint32_t ntiles) {
+    const uint32_t k = tile / kRoundTiles;
+    st_status(ws.status + tile, kPublished | count);
+    const uint32_t left = ntiles - k * kRoundTiles, members = left < kRoundTiles ? left : kRoundTiles;
+    const unsigned long long old = atomicAdd(ws.round_acc + k, (1ull << 48) | count);
+    if ((uint32_t)(old >> 48) == members - 1) {  // this tile completes round k
+        unsigned long long base = kPublished;
+        if (k) do base = ld_status(ws.round_prefix + k); while (!(base & kPublished));
+        st_status(ws.round_prefix + k + 1, base + (old & kRoundSumMask) + count);
     }
+}
+
+// One full warp: first vertex id of `tile` (waits for the tiles before it in its round and for the round's
+// prefix).  Also valid as a pure re-read after the scan has completed (vertices-only pass).
+__device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspace &ws, uint32_t tile, int lane) {
+    const uint32_t k = tile / kRoundTiles, j = tile % kRoundTiles;
     unsigned long long s[kRoundTiles / 32];
     const unsigned long long *st = ws.status + (tile - j);
 #pragma unroll
@@ -118,17 +121,25 @@ __device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspac
 //   stage      fp32 samples of a tile: rows (xi, yi) of 0..8 x 0..8, kBoxZ samples each (TMA box)
 //   sbits      [81][8] words: inside bits of every staged row (word 4, bit 0 = the halo sample)
 //   piece      [64] vertex count of each owned (row, piece)
-//   list       compacted crossing edges of the tile: axis<<13 | row<<7 | z
-// A thread owns bit word (row r = tid>>2, word w = tid&3) of the tile in the count phase.
+//   list, dt   per warp: the crossing edges of the warp's 8 rows (axis<<13 | row<<7 | z) and their
+//              interpolation parameters
+// A thread owns bit word (row r = tid>>2, word w = tid&3) of the tile in the count phase; a warp owns the 8
+// rows of one plane, whose vertices are a contiguous id range of the tile.
+//
+// Per tile: bits -> counts -> tile scan -> publish count -> per warp: compact edges, interpolate dt from the
+// staged samples -> the stage is free: the NEXT tile's TMA load is issued -> wait for the tile's first
+// vertex id -> write vertices (position = integer corner + dt on one axis) and the table entries.  The
+// load of the next tile and the wait for the scan overlap.
 // ---------------------------------------------------------------------------------------------
-constexpr int kListCap = 2048;
+constexpr int kWarpCap = 128;   // pending crossing edges per warp
 constexpr int kSbitsStride = 8;
 constexpr int kRowPitch = kTileY + 1;  // staged rows per plane
 
 struct TileSmem {
     uint32_t sbits[kBoxRows * kSbitsStride];
     uint32_t piece[kTileX * kTileY];
-    uint16_t list[kListCap];
+    float dt[kTileThreads / 32][kWarpCap];
+    uint16_t list[kTileThreads / 32][kWarpCap];
     uint8_t ntri[256];  // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
     unsigned long long bar;
     unsigned long long tile_base;
@@ -160,41 +171,72 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                             ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
         S.ntri[c] = (uint8_t)(c_case_table[cs] >> 60);
     }
-    if (TMA && tid == 0) {
-        mbar_init(smem_u32(&S.bar), 1);
-        mbar_fence_init();
+
+    // Tile id -> coordinates, TMA load (one thread).  CTA b takes tiles b, b + gridDim, b + 2 gridDim, ...: all
+    // CTAs are resident (the grid is sized by occupancy), so the tiles before any tile of a sweep are being
+    // processed at the same time as it -- the scan below never waits for a tile that is parked behind another.
+    // Tiles are ordered band by band (a band = `band`
+    // y-blocks over all x), inside a band x-block major, then y-block, then piece: the x halo plane of a block
+    // is re-read from L2, not HBM.
+    auto fetch = [&](uint32_t t) {
+        int4 c = make_int4(0, 0, 0, (int)t);
+        if (t < ntiles) {
+            const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
+            const uint32_t bi = t / per_band, rem = t - bi * per_band;
+            const uint32_t left = (uint32_t)g.nyb - bi * (uint32_t)g.band, cur = left < (uint32_t)g.band ? left : (uint32_t)g.band;
+            const uint32_t xb = rem / (cur * np), rem2 = rem - xb * (cur * np);
+            const uint32_t yb = rem2 / np, p = rem2 - yb * np;
+            c.x = (int)(xb * kTileX), c.y = (int)((bi * g.band + yb) * kTileY), c.z = (int)p;
+            if (TMA) {
+                const uint32_t bar = smem_u32(&S.bar);
+                mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
+                tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
+            }
+        }
+        S.coord = c;
+    };
+    if (tid == 0) {
+        if (TMA) {
+            mbar_init(smem_u32(&S.bar), 1);
+            mbar_fence_init();
+        }
+        fetch(blockIdx.x);
     }
+    __syncthreads();
 
     // my word of the tile (count phase): row r = (xi, yi), word w
     const int r = tid >> 2, w = tid & 3;
     const int xi = r >> 3, yi = r & 7;
-    const int ra = xi * kRowPitch + yi;
-    const uint32_t *sa = &S.sbits[ra * kSbitsStride + w];
+    const uint32_t *sa = &S.sbits[(xi * kRowPitch + yi) * kSbitsStride + w];
     const int64_t bstride = 4 * (int64_t)np;  // bit words per row
+    uint16_t *wlist = S.list[warp];
+    float *wdt = S.dt[warp];
+
+    // one crossing edge -> its vertex (gen_vertices_kernel :70-138 and the epilogue :298)
+    auto edge_dt = [&](uint32_t ent) {
+        const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
+        const float *src = tf + ((er >> 3) * kRowPitch + (er & 7u)) * kBoxZ + ez;
+        const float d0 = src[0];
+        const float d1 = src[ax == 0 ? kRowPitch * kBoxZ : (ax == 1 ? kBoxZ : 1)];
+        // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
+        return __fdiv_rn(__fsub_rn(thresh, d0), __fsub_rn(d1, d0));
+    };
+    auto put_vertex = [&](unsigned long long id, uint32_t ent, float dt, int x0, int y0, int z0) {
+        const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
+        float px = (float)(xg0 + x0 + (int)(er >> 3));  // static_cast<float>(x), :107
+        float py = (float)(y0 + (int)(er & 7u));
+        float pz = (float)(z0 + (int)ez);
+        if (ax == 0) px = __fadd_rn(px, dt);
+        if (ax == 1) py = __fadd_rn(py, dt);
+        if (ax == 2) pz = __fadd_rn(pz, dt);
+        // vertices * scale + offset as two separately rounded ops (:298)
+        float *out = verts + id * 3ull;
+        out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
+        out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
+        out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
+    };
 
     for (uint32_t it = 0;; ++it) {
-        // ---- next tile: id -> coordinates, TMA load.  Tiles are ordered band by band (a band = `band` y-blocks
-        // over all x), inside a band x-block major, then y-block, then piece: the x halo plane of a block is
-        // re-read from L2, not HBM ----
-        if (tid == 0) {
-            const uint32_t t = atomicAdd(&ws.header->ticket, 1u);
-            int4 c = make_int4(0, 0, 0, (int)t);
-            if (t < ntiles) {
-                const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
-                const uint32_t bi = t / per_band, rem = t - bi * per_band;
-                const uint32_t left = (uint32_t)g.nyb - bi * (uint32_t)g.band, cur = left < (uint32_t)g.band ? left : (uint32_t)g.band;
-                const uint32_t xb = rem / (cur * np), rem2 = rem - xb * (cur * np);
-                const uint32_t yb = rem2 / np, p = rem2 - yb * np;
-                c.x = (int)(xb * kTileX), c.y = (int)((bi * g.band + yb) * kTileY), c.z = (int)p;
-                if (TMA) {
-                    const uint32_t bar = smem_u32(&S.bar);
-                    mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
-                    tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
-                }
-            }
-            S.coord = c;
-        }
-        __syncthreads();
         const int4 tc = S.coord;
         const uint32_t tile = (uint32_t)tc.w;
         if (tile >= ntiles) break;
@@ -233,7 +275,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
             }
         }
-        __syncthreads();
+        __syncthreads();  // [bits]
 
         // ---- phase 2: crossing masks and counts of my word ----
         const int x = x0 + xi, y = y0 + yi;
@@ -284,10 +326,11 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * bstride + 4 * p + (tid & 3)] =
                     S.sbits[(kTileX * kRowPitch + (tid >> 2)) * kSbitsStride + (tid & 3)];
         }
-        __syncthreads();
+        __syncthreads();  // [count]
 
         // ---- tile scan (every warp redundantly): first vertex of each (row, piece), relative to the tile ----
-        uint32_t vt, pe;
+        uint32_t vt, pe, wbase, wcount;
+        bool fast;
         {
             const uint2 v = *reinterpret_cast<const uint2 *>(&S.piece[2 * lane]);
             const uint32_t s2 = v.x + v.y, incl = warp_incl_scan(s2, lane);
@@ -295,60 +338,87 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             const uint32_t e0 = incl - s2;
             const uint32_t g0 = __shfl_sync(kFull, e0, r >> 1), g1 = __shfl_sync(kFull, v.x, r >> 1);
             pe = g0 + ((r & 1) ? g1 : 0u);
+            // vertices of warp k's 8 rows: [e0 of lane 4k, e0 of lane 4k+4)
+            const uint32_t nxt = __shfl_down_sync(kFull, e0, 4);
+            const uint32_t seg = ((lane & 3) == 0) ? (lane == 28 ? vt : nxt) - e0 : 0u;
+            fast = !__any_sync(kFull, seg > (uint32_t)kWarpCap);
+            wbase = __shfl_sync(kFull, e0, 4 * warp);
+            wcount = __shfl_sync(kFull, seg, 4 * warp);
         }
+        if (mode == 0 && tid == 0) tile_publish(ws, tile, vt, ntiles);
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
-        const uint32_t wfirst[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
+        const uint32_t wfirst[3] = {vx_rel + (exw & 255u) - wbase, vy_rel + ((exw >> 8) & 255u) - wbase,
+                                    vz_rel + (exw >> 16) - wbase};  // relative to my warp's first vertex
         const uint32_t wmask[3] = {m0, m1, m2};
+        const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
 
-        // ---- first vertex id of the tile (warp 0) ----
-        if (warp == 0) {
-            const unsigned long long tb = tile_first_vertex(ws, tile, vt, ntiles, mode == 0, lane);
-            if (lane == 0) {
-                S.tile_base = tb;
-                if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
-            }
-        }
-
-        // ---- vertices: compact the crossing edges, then one edge per thread (gen_vertices_kernel :70-138) ----
-        for (uint32_t c0 = 0; c0 < vt || c0 == 0; c0 += kListCap) {
+        if (fast) {
+            // ---- my warp's crossing edges: compact, interpolate; then the stage is free ----
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
-                uint32_t pos = wfirst[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
+                uint32_t pos = wfirst[ax];
                 for (uint32_t rem = wmask[ax]; rem; ++pos) {
                     const int i = __ffs(rem) - 1;
                     rem &= rem - 1;
-                    if (pos < (uint32_t)kListCap) S.list[pos] = (uint16_t)((ax << 13) | (r << 7) | (w << 5) | i);
+                    wlist[pos] = (uint16_t)((ax << 13) | ecode | i);
                 }
             }
-            __syncthreads();  // list complete; S.tile_base visible
-            const unsigned long long tb = S.tile_base;
-            if (c0 == 0 && mode == 0 && own && w == 0)
-                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
-            const uint32_t n = vt - c0 < (uint32_t)kListCap ? vt - c0 : (uint32_t)kListCap;
-            for (uint32_t k = tid; k < n && vt > c0; k += kTileThreads) {
-                const unsigned long long id = tb + c0 + k;
-                if (id >= vcap) continue;
-                const uint32_t ent = S.list[k];
-                const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
-                const uint32_t exi = er >> 3, eyi = er & 7u;
-                const float *src = tf + (exi * kRowPitch + eyi) * kBoxZ + ez;
-                const float d0 = src[0];
-                const float d1 = src[ax == 0 ? kRowPitch * kBoxZ : (ax == 1 ? kBoxZ : 1)];
-                // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
-                const float dt = __fdiv_rn(__fsub_rn(thresh, d0), __fsub_rn(d1, d0));
-                float px = (float)(xg0 + x0 + (int)exi);  // static_cast<float>(x), :107
-                float py = (float)(y0 + (int)eyi);
-                float pz = (float)(z0 + (int)ez);
-                if (ax == 0) px = __fadd_rn(px, dt);
-                if (ax == 1) py = __fadd_rn(py, dt);
-                if (ax == 2) pz = __fadd_rn(pz, dt);
-                // vertices * scale + offset as two separately rounded ops (:298)
-                float *out = verts + id * 3ull;
-                out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
-                out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
-                out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
+            __syncwarp();
+            for (uint32_t k = lane; k < wcount; k += 32) wdt[k] = edge_dt(wlist[k]);
+            __syncthreads();  // [stage free]
+            if (tid == 32) fetch(tile + gridDim.x);
+            if (warp == 0) {
+                const unsigned long long tb = tile_first_vertex(ws, tile, lane);
+                if (lane == 0) {
+                    S.tile_base = tb;
+                    if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
+                }
             }
-            __syncthreads();  // the list (next chunk) and the stage (next tile) may be overwritten
+            __syncthreads();  // [tile base]
+            const unsigned long long tb = S.tile_base;
+            if (mode == 0 && own && w == 0)
+                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
+            for (uint32_t k = lane; k < wcount; k += 32) {
+                const unsigned long long id = tb + wbase + k;
+                if (id < vcap) put_vertex(id, wlist[k], wdt[k], x0, y0, z0);
+            }
+            __syncwarp();  // my warp's list is rewritten by the next tile
+        } else {
+            // ---- a warp has more crossings than its pending list holds (noise-like data): keep the stage,
+            // wait for the tile's first id, and emit chunk by chunk ----
+            if (warp == 0) {
+                const unsigned long long tb = tile_first_vertex(ws, tile, lane);
+                if (lane == 0) {
+                    S.tile_base = tb;
+                    if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
+                }
+            }
+            __syncthreads();  // [tile base]
+            const unsigned long long tb = S.tile_base;
+            if (mode == 0 && own && w == 0)
+                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
+            for (uint32_t c0 = 0; c0 < wcount; c0 += kWarpCap) {
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    uint32_t pos = wfirst[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
+                    for (uint32_t rem = wmask[ax]; rem; ++pos) {
+                        const int i = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        if (pos < (uint32_t)kWarpCap) wlist[pos] = (uint16_t)((ax << 13) | ecode | i);
+                    }
+                }
+                __syncwarp();
+                const uint32_t n = wcount - c0 < (uint32_t)kWarpCap ? wcount - c0 : (uint32_t)kWarpCap;
+                for (uint32_t k = lane; k < n; k += 32) {
+                    const unsigned long long id = tb + wbase + c0 + k;
+                    const uint32_t ent = wlist[k];
+                    if (id < vcap) put_vertex(id, ent, edge_dt(ent), x0, y0, z0);
+                }
+                __syncwarp();
+            }
+            __syncthreads();  // [stage free]
+            if (tid == 32) fetch(tile + gridDim.x);
+            __syncthreads();  // [next tile known]
         }
     }
 }
@@ -692,7 +762,13 @@ void launch_tile_kernel(const CUtensorMap &map, const float *grid, const McGeom 
         return true;
     }();
     (void)attr;
-    const int64_t cap = (int64_t)sm_count() * 4;
+    // every CTA must be resident: tiles are assigned round-robin and wait for lower tile ids
+    static const int per_sm = [] {
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA>, kTileThreads, kTileSmemBytes);
+        return n > 0 ? n : 1;
+    }();
+    const int64_t cap = (int64_t)sm_count() * per_sm;
     const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
     k_tile<TMA><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, grid, g, ws, p, verts,
                                                              (unsigned long long)(vcap > 0 ? vcap : 0), mode);
