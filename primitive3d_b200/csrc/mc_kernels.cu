@@ -92,25 +92,31 @@ __device__ __forceinline__ void tile_publish(const McWorkspace &ws, uint32_t til
     }
 }
 
-// One full warp: first vertex id of `tile` (waits for the tiles before it in its round and for the round's
-// prefix).  Also valid as a pure re-read after the scan has completed (vertices-only pass).
-__device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspace &ws, uint32_t tile, int lane) {
+// One full warp: first vertex id of `tile`.  Blocking: waits for the tiles before it in its round and for the
+// round's prefix.  Non-blocking: returns false if any of them is not published yet.  Also valid as a pure
+// re-read after the scan has completed (vertices-only pass).
+template <bool BLOCK>
+__device__ __forceinline__ bool tile_first_vertex(const McWorkspace &ws, uint32_t tile, int lane, unsigned long long &first) {
     const uint32_t k = tile / kRoundTiles, j = tile % kRoundTiles;
     unsigned long long s[kRoundTiles / 32];
     const unsigned long long *st = ws.status + (tile - j);
 #pragma unroll
     for (int i = 0; i < (int)kRoundTiles / 32; ++i) s[i] = (uint32_t)(lane + 32 * i) < j ? ld_status(st + lane + 32 * i) : kPublished;
-    unsigned long long acc = 0;
+    unsigned long long acc = kPublished, ready = kPublished;
     if (lane == 0 && k) {
-        do acc = ld_status(ws.round_prefix + k); while (!(acc & kPublished));
-        acc &= ~kPublished;
+        acc = ld_status(ws.round_prefix + k);
+        if (BLOCK) while (!(acc & kPublished)) acc = ld_status(ws.round_prefix + k);
+        ready = acc;
     }
 #pragma unroll
     for (int i = 0; i < (int)kRoundTiles / 32; ++i) {
-        while (!(s[i] & kPublished)) s[i] = ld_status(st + lane + 32 * i);
+        if (BLOCK) while (!(s[i] & kPublished)) s[i] = ld_status(st + lane + 32 * i);
+        ready &= s[i];
         acc += s[i] & ~kPublished;
     }
-    return warp_sum64(acc);
+    if (!BLOCK && !__all_sync(kFull, (ready & kPublished) != 0ull)) return false;
+    first = warp_sum64(acc & ~kPublished);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -131,19 +137,29 @@ __device__ __forceinline__ unsigned long long tile_first_vertex(const McWorkspac
 // vertex id -> write vertices (position = integer corner + dt on one axis) and the table entries.  The
 // load of the next tile and the wait for the scan overlap.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWarpCap = 128;   // pending crossing edges per warp
+constexpr int kRing = 1728;     // pending crossing edges of a CTA (6 bytes each): ~5 tiles of the gyroid case
+constexpr int kQueue = 8;       // pending tiles of a CTA
 constexpr int kSbitsStride = 8;
 constexpr int kRowPitch = kTileY + 1;  // staged rows per plane
+
+struct PendingTile {
+    int4 coord;            // {x0, y0, piece, tile}
+    uint32_t start, count; // its entries in the ring
+    uint32_t pad[2];
+};
 
 struct TileSmem {
     uint32_t sbits[kBoxRows * kSbitsStride];
     uint32_t piece[kTileX * kTileY];
-    float dt[kTileThreads / 32][kWarpCap];
-    uint16_t list[kTileThreads / 32][kWarpCap];
-    uint8_t ntri[256];  // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
+    float dt[kRing];       // pending vertices: interpolation parameter ...
+    uint16_t ent[kRing];   // ... and edge (axis<<13 | row<<7 | z)
+    uint8_t ntri[256];     // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
+    PendingTile q[kQueue];
     unsigned long long bar;
-    unsigned long long tile_base;
-    int4 coord;         // {x0, y0, piece, tile}
+    unsigned long long base;       // result of warp 0's non-blocking look-back at the top of an iteration
+    unsigned long long base_wait;  // result of a blocking look-back
+    uint32_t base_ok;
+    int4 coord[2];         // {x0, y0, piece, tile} of the tile of iteration it, by parity
 };
 constexpr int kTileSmemBytes = kStageBytes + (int)sizeof(TileSmem) + 128;
 
@@ -172,13 +188,9 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         S.ntri[c] = (uint8_t)(c_case_table[cs] >> 60);
     }
 
-    // Tile id -> coordinates, TMA load (one thread).  CTA b takes tiles b, b + gridDim, b + 2 gridDim, ...: all
-    // CTAs are resident (the grid is sized by occupancy), so the tiles before any tile of a sweep are being
-    // processed at the same time as it -- the scan below never waits for a tile that is parked behind another.
-    // Tiles are ordered band by band (a band = `band`
-    // y-blocks over all x), inside a band x-block major, then y-block, then piece: the x halo plane of a block
-    // is re-read from L2, not HBM.
-    auto fetch = [&](uint32_t t) {
+    // Tile id -> coordinates.  Tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
+    // band x-block major, then y-block, then piece: the x halo plane of a block is re-read from L2, not HBM.
+    auto locate = [&](uint32_t t) {
         int4 c = make_int4(0, 0, 0, (int)t);
         if (t < ntiles) {
             const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
@@ -187,20 +199,24 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             const uint32_t xb = rem / (cur * np), rem2 = rem - xb * (cur * np);
             const uint32_t yb = rem2 / np, p = rem2 - yb * np;
             c.x = (int)(xb * kTileX), c.y = (int)((bi * g.band + yb) * kTileY), c.z = (int)p;
-            if (TMA) {
-                const uint32_t bar = smem_u32(&S.bar);
-                mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
-                tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
-            }
         }
-        S.coord = c;
+        return c;
+    };
+    auto issue = [&](const int4 &c) {  // one thread, once the stage is free
+        if (TMA && (uint32_t)c.w < ntiles) {
+            const uint32_t bar = smem_u32(&S.bar);
+            mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
+            tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
+        }
     };
     if (tid == 0) {
         if (TMA) {
             mbar_init(smem_u32(&S.bar), 1);
             mbar_fence_init();
         }
-        fetch(blockIdx.x);
+        const int4 c = locate(atomicAdd(&ws.header->ticket, 1u));
+        S.coord[0] = c;
+        issue(c);
     }
     __syncthreads();
 
@@ -209,8 +225,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     const int xi = r >> 3, yi = r & 7;
     const uint32_t *sa = &S.sbits[(xi * kRowPitch + yi) * kSbitsStride + w];
     const int64_t bstride = 4 * (int64_t)np;  // bit words per row
-    uint16_t *wlist = S.list[warp];
-    float *wdt = S.dt[warp];
 
     // one crossing edge -> its vertex (gen_vertices_kernel :70-138 and the epilogue :298)
     auto edge_dt = [&](uint32_t ent) {
@@ -236,11 +250,66 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
     };
 
+    // Emission of a tile is deferred: its first vertex id needs the counts of every tile before it.  The
+    // crossing edges of a counted tile (edge code + interpolation parameter, 6 bytes) wait in a ring in shared
+    // memory; the oldest pending tile is retired when a non-blocking look-back finds its first id, or -- only
+    // when the ring is full -- after a blocking one.  A CTA therefore (almost) never waits for another CTA.
+    // Queue state, identical in every thread:
+    uint32_t q_head = 0, q_count = 0, ring_used = 0, ring_tail = 0;
+
+    // vertices of the pending tile in queue slot `slot`, whose first vertex id is `base`
+    auto retire = [&](uint32_t slot, unsigned long long base) {
+        const int4 c = S.q[slot].coord;
+        const uint32_t start = S.q[slot].start, count = S.q[slot].count;
+        if (tid == 0 && mode == 0) {
+            ws.tbase[c.w] = (uint32_t)base;
+            if ((uint32_t)c.w == ntiles - 1) ws.header->total_v = base + count;
+        }
+        for (uint32_t k = tid; k < count; k += kTileThreads) {
+            uint32_t idx = start + k;
+            if (idx >= (uint32_t)kRing) idx -= kRing;
+            const unsigned long long id = base + k;
+            if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
+        }
+        ring_used -= count;
+        q_head = (q_head + 1) % kQueue;
+        --q_count;
+    };
+    // blocking look-back for `tile` by warp 0, result to every thread (two barriers)
+    auto wait_base = [&](uint32_t t) {
+        if (warp == 0) {
+            unsigned long long tb = 0;
+            tile_first_vertex<true>(ws, t, lane, tb);
+            if (lane == 0) S.base_wait = tb;
+        }
+        __syncthreads();
+        const unsigned long long tb = S.base_wait;
+        __syncthreads();
+        return tb;
+    };
+
     for (uint32_t it = 0;; ++it) {
-        const int4 tc = S.coord;
+        const int4 tc = S.coord[it & 1u];
         const uint32_t tile = (uint32_t)tc.w;
         if (tile >= ntiles) break;
         const int x0 = tc.x, y0 = tc.y, p = tc.z, z0 = p * kTileZ;
+
+        // ticket of this CTA's next tile, asked for a whole tile ahead of its use.  Tiles are handed out in
+        // increasing order to running CTAs: every tile before a tile is finished or in flight, whatever the
+        // residency of the grid, and a CTA that got a light tile simply takes the next one sooner.
+        uint32_t next_tile = 0;
+        if (tid == 32) next_tile = atomicAdd(&ws.header->ticket, 1u);
+
+        // first vertex id of the oldest pending tile, asked for while this tile's load is in flight: the round
+        // trip to L2 hides behind the TMA wait.  Non-blocking.
+        if (q_count && warp == 0) {
+            unsigned long long tb = 0;
+            const bool ok = tile_first_vertex<false>(ws, (uint32_t)S.q[q_head].coord.w, lane, tb);
+            if (lane == 0) {
+                S.base_ok = ok ? 1u : 0u;
+                S.base = tb;
+            }
+        }
 
         if (TMA) {
             mbar_wait(smem_u32(&S.bar), it & 1u);
@@ -330,7 +399,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
 
         // ---- tile scan (every warp redundantly): first vertex of each (row, piece), relative to the tile ----
         uint32_t vt, pe, wbase, wcount;
-        bool fast;
         {
             const uint2 v = *reinterpret_cast<const uint2 *>(&S.piece[2 * lane]);
             const uint32_t s2 = v.x + v.y, incl = warp_incl_scan(s2, lane);
@@ -341,85 +409,107 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             // vertices of warp k's 8 rows: [e0 of lane 4k, e0 of lane 4k+4)
             const uint32_t nxt = __shfl_down_sync(kFull, e0, 4);
             const uint32_t seg = ((lane & 3) == 0) ? (lane == 28 ? vt : nxt) - e0 : 0u;
-            fast = !__any_sync(kFull, seg > (uint32_t)kWarpCap);
             wbase = __shfl_sync(kFull, e0, 4 * warp);
             wcount = __shfl_sync(kFull, seg, 4 * warp);
         }
         if (mode == 0 && tid == 0) tile_publish(ws, tile, vt, ntiles);
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
-        const uint32_t wfirst[3] = {vx_rel + (exw & 255u) - wbase, vy_rel + ((exw >> 8) & 255u) - wbase,
-                                    vz_rel + (exw >> 16) - wbase};  // relative to my warp's first vertex
+        // table entry of my (row, piece): first ids relative to the tile + the tile, whose first id lands in tbase
+        if (mode == 0 && own && w == 0) ws.ptab[grow * np + p] = make_uint4(vx_rel, vy_rel, vz_rel, tile);
+        const uint32_t first[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
         const uint32_t wmask[3] = {m0, m1, m2};
         const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
+        // the look-back result of the top of this iteration (read before warp 0 can overwrite it)
+        bool probe_ok = q_count && S.base_ok;
+        const unsigned long long probe_base = S.base;
 
-        if (fast) {
-            // ---- my warp's crossing edges: compact, interpolate; then the stage is free ----
+        if (vt <= (uint32_t)kRing) {
+            // ---- make room in the ring (rare): retire the oldest pending tiles, waiting for their ids ----
+            while (q_count && (ring_used + vt > (uint32_t)kRing || q_count == (uint32_t)kQueue)) {
+                unsigned long long tb = probe_base;
+                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].coord.w);
+                probe_ok = false;
+                retire(q_head, tb);
+                __syncthreads();  // its entries may be overwritten now
+            }
+            // ---- my crossing edges -> ring; my warp interpolates its own (contiguous) range ----
+            const uint32_t start = ring_tail;
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
-                uint32_t pos = wfirst[ax];
-                for (uint32_t rem = wmask[ax]; rem; ++pos) {
+                uint32_t pos = start + first[ax];
+                if (pos >= (uint32_t)kRing) pos -= kRing;
+                for (uint32_t rem = wmask[ax]; rem;) {
                     const int i = __ffs(rem) - 1;
                     rem &= rem - 1;
-                    wlist[pos] = (uint16_t)((ax << 13) | ecode | i);
+                    S.ent[pos] = (uint16_t)((ax << 13) | ecode | i);
+                    if (++pos == (uint32_t)kRing) pos = 0;
                 }
             }
             __syncwarp();
-            for (uint32_t k = lane; k < wcount; k += 32) wdt[k] = edge_dt(wlist[k]);
-            __syncthreads();  // [stage free]
-            if (tid == 32) fetch(tile + gridDim.x);
-            if (warp == 0) {
-                const unsigned long long tb = tile_first_vertex(ws, tile, lane);
-                if (lane == 0) {
-                    S.tile_base = tb;
-                    if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
-                }
-            }
-            __syncthreads();  // [tile base]
-            const unsigned long long tb = S.tile_base;
-            if (mode == 0 && own && w == 0)
-                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
             for (uint32_t k = lane; k < wcount; k += 32) {
-                const unsigned long long id = tb + wbase + k;
-                if (id < vcap) put_vertex(id, wlist[k], wdt[k], x0, y0, z0);
+                uint32_t idx = start + wbase + k;
+                if (idx >= (uint32_t)kRing) idx -= kRing;
+                S.dt[idx] = edge_dt(S.ent[idx]);
             }
-            __syncwarp();  // my warp's list is rewritten by the next tile
+            if (tid == 0) {
+                PendingTile &q = S.q[(q_head + q_count) % kQueue];
+                q.coord = tc;
+                q.start = start;
+                q.count = vt;
+            }
+            ++q_count;
+            ring_used += vt;
+            ring_tail = start + vt >= (uint32_t)kRing ? start + vt - kRing : start + vt;
         } else {
-            // ---- a warp has more crossings than its pending list holds (noise-like data): keep the stage,
-            // wait for the tile's first id, and emit chunk by chunk ----
-            if (warp == 0) {
-                const unsigned long long tb = tile_first_vertex(ws, tile, lane);
-                if (lane == 0) {
-                    S.tile_base = tb;
-                    if (mode == 0 && tile == ntiles - 1) ws.header->total_v = tb + vt;
-                }
+            // ---- more crossings than the ring holds (noise-like data): retire everything pending, wait for
+            // this tile's first id, and emit it chunk by chunk from the stage ----
+            while (q_count) {
+                unsigned long long tb = probe_base;
+                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].coord.w);
+                probe_ok = false;
+                retire(q_head, tb);
             }
-            __syncthreads();  // [tile base]
-            const unsigned long long tb = S.tile_base;
-            if (mode == 0 && own && w == 0)
-                ws.ptab[grow * np + p] = make_uint4((uint32_t)tb + vx_rel, (uint32_t)tb + vy_rel, (uint32_t)tb + vz_rel, nf);
-            for (uint32_t c0 = 0; c0 < wcount; c0 += kWarpCap) {
+            const unsigned long long tb = wait_base(tile);
+            if (tid == 0 && mode == 0) {
+                ws.tbase[tile] = (uint32_t)tb;
+                if (tile == ntiles - 1) ws.header->total_v = tb + vt;
+            }
+            for (uint32_t c0 = 0; c0 < vt; c0 += kRing) {
 #pragma unroll
                 for (int ax = 0; ax < 3; ++ax) {
-                    uint32_t pos = wfirst[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
+                    uint32_t pos = first[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
                     for (uint32_t rem = wmask[ax]; rem; ++pos) {
                         const int i = __ffs(rem) - 1;
                         rem &= rem - 1;
-                        if (pos < (uint32_t)kWarpCap) wlist[pos] = (uint16_t)((ax << 13) | ecode | i);
+                        if (pos < (uint32_t)kRing) S.ent[pos] = (uint16_t)((ax << 13) | ecode | i);
                     }
                 }
-                __syncwarp();
-                const uint32_t n = wcount - c0 < (uint32_t)kWarpCap ? wcount - c0 : (uint32_t)kWarpCap;
-                for (uint32_t k = lane; k < n; k += 32) {
-                    const unsigned long long id = tb + wbase + c0 + k;
-                    const uint32_t ent = wlist[k];
+                __syncthreads();
+                const uint32_t n = vt - c0 < (uint32_t)kRing ? vt - c0 : (uint32_t)kRing;
+                for (uint32_t k = tid; k < n; k += kTileThreads) {
+                    const unsigned long long id = tb + c0 + k;
+                    const uint32_t ent = S.ent[k];
                     if (id < vcap) put_vertex(id, ent, edge_dt(ent), x0, y0, z0);
                 }
-                __syncwarp();
+                __syncthreads();
             }
-            __syncthreads();  // [stage free]
-            if (tid == 32) fetch(tile + gridDim.x);
-            __syncthreads();  // [next tile known]
+            ring_tail = 0;
         }
+        // the next tile's coordinates are published before the barrier, its load is issued after it
+        int4 nc = make_int4(0, 0, 0, 0);
+        if (tid == 32) {
+            nc = locate(next_tile);
+            S.coord[(it + 1u) & 1u] = nc;
+        }
+        __syncthreads();  // [stage free]
+        if (tid == 32) issue(nc);
+
+        // ---- the oldest pending tile, if the look-back at the top of this iteration found its first id ----
+        if (probe_ok) retire(q_head, probe_base);
+    }
+    while (q_count) {  // the tiles still pending
+        const unsigned long long tb = wait_base((uint32_t)S.q[q_head].coord.w);
+        retire(q_head, tb);
     }
 }
 
@@ -560,23 +650,31 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 5)
         }
         const bool hc = valid && (x + 1 < rx) && (y + 1 < ry);
         uint4 ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
+        // a table entry holds ids relative to its tile; .w names the tile, tbase[] its first vertex id
+        auto entry = [&](int64_t i) {
+            uint4 t = ws.ptab[i];
+            const uint32_t b = ws.tbase[t.w];
+            t.x += b, t.y += b, t.z += b;
+            return t;
+        };
+        uint32_t nf = 0;
         if (hc) {
-            ta = ws.ptab[gi];
-            tb = ws.ptab[gi + plane_pieces];
-            td = ws.ptab[gi + np];
-            tcc = ws.ptab[gi + plane_pieces + np];
+            nf = ws.nf[gi];
+            ta = entry(gi);
+            tb = entry(gi + plane_pieces);
+            td = entry(gi + np);
+            tcc = entry(gi + plane_pieces + np);
         }
-        const uint32_t nf = hc ? ta.w : 0u;
         if (!__any_sync(kFull, nf != 0u)) continue;
 
         // entries of the next piece of the same rows: the cell at bit 127 reads its z+1 edges there
         uint32_t nax = __shfl_down_sync(kFull, ta.x, 2), nay = __shfl_down_sync(kFull, ta.y, 2);
         uint32_t nby = __shfl_down_sync(kFull, tb.y, 2), ndx = __shfl_down_sync(kFull, td.x, 2);
         if (lane >= 30 && hc && p + 1 < np) {
-            const uint4 t0 = ws.ptab[gi + 1];
+            const uint4 t0 = entry(gi + 1);
             nax = t0.x, nay = t0.y;
-            nby = ws.ptab[gi + 1 + plane_pieces].y;
-            ndx = ws.ptab[gi + 1 + np].x;
+            nby = entry(gi + 1 + plane_pieces).y;
+            ndx = entry(gi + 1 + np).x;
         }
         unsigned long long fbase = 0;
         if (lane == 0) fbase = ws.f8[grp * (kFacePieces / 8)];
@@ -829,18 +927,37 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces);
 }
 
-// Multi-GPU: install the next shard's first-plane table as this shard's halo-plane numbering.
-__global__ void k_import_halo(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, uint32_t delta) {
+// Multi-GPU.  Export: the first plane's table entries with absolute (shard-local) ids.  Import: install the next
+// shard's first-plane entries, shifted by this shard's vertex count, as this shard's halo-plane numbering; they
+// name the extra tile slot `ntiles`, whose tbase stays 0.
+__global__ void k_export_plane(uint4 *__restrict__ dst, const uint4 *__restrict__ ptab, const uint32_t *__restrict__ tbase, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const uint4 t = src[i];
-        dst[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, t.w);
+        const uint4 t = ptab[i];
+        const uint32_t b = tbase[t.w];
+        dst[i] = make_uint4(t.x + b, t.y + b, t.z + b, 0u);
     }
 }
 
-void launch_import_halo(uint4 *halo_entries, const uint32_t *table_in, int64_t n, uint32_t delta, cudaStream_t s) {
+__global__ void k_import_halo(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, uint32_t delta, uint32_t slot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint4 t = src[i];
+        dst[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, slot);
+    }
+}
+
+void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
+    const int64_t n = g.ry * (int64_t)g.np;
     if (n <= 0) return;
-    k_import_halo<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(halo_entries, reinterpret_cast<const uint4 *>(table_in), n, delta);
+    k_export_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(table_out), ws.ptab, ws.tbase, n);
+}
+
+void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s) {
+    const int64_t n = g.ry * (int64_t)g.np;
+    if (n <= 0) return;
+    k_import_halo<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.ptab + g.owned_x * n, reinterpret_cast<const uint4 *>(table_in), n,
+                                                              delta, (uint32_t)g.ntiles);
 }
 
 }  // namespace p3d

@@ -65,7 +65,9 @@ struct McWorkspace {
     unsigned long long *round_acc;     // [nrounds] arrivals<<48 | vertex count of each round of 256 tiles
     unsigned long long *round_prefix;  // [nrounds + 1] published exclusive vertex prefix of each round
     unsigned long long *status_f;  // [nscan]  look-back status words of k_fscan
-    uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: first ids of the piece's x/y/z-edge vertices, #triangles
+    uint32_t *tbase;               // [ntiles + 1] first vertex id of each tile (slot ntiles: imported halo entries, 0)
+    uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, tile}: first ids of the piece's x/y/z-edge vertices relative to
+                                   // its tile, and the tile
     uint32_t *nf;                  // [npieces] triangles per piece (input of k_fscan)
     unsigned long long *f8;        // [ceil(npieces/8)] index of the first face of pieces 8i..
     uint32_t *bits;                // [rx*ry][4*np] inside bits, 32 samples per word
@@ -85,7 +87,8 @@ void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws,
                       int64_t vertex_capacity, int mode, cudaStream_t s);
 void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s);
-void launch_import_halo(uint4 *halo_entries, const uint32_t *table_in, int64_t n, uint32_t delta, cudaStream_t s);
+void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
+void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor
 
 }  // namespace p3d

@@ -56,7 +56,7 @@ bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
 }
 
 struct Layout {
-    size_t header, status, round_acc, round_prefix, status_f, zero_end, ptab, nf, f8, bits, total;
+    size_t header, status, round_acc, round_prefix, status_f, tbase, zero_end, ptab, nf, f8, bits, total;
 };
 
 Layout make_layout(const p3d::McGeom &g) {
@@ -68,6 +68,7 @@ Layout make_layout(const p3d::McGeom &g) {
     l.round_acc = off;    off += align_up((size_t)g.nrounds * 8);
     l.round_prefix = off; off += align_up((size_t)(g.nrounds + 1) * 8);
     l.status_f = off; off += align_up((size_t)g.nscan * 8);
+    l.tbase = off;    off += align_up(((size_t)g.ntiles + 1) * 4);
     l.zero_end = off;  // everything above is zeroed before a count
     l.ptab = off;     off += align_up(all_pieces * sizeof(uint4));
     l.nf = off;       off += align_up((size_t)g.npieces * 4 + 32);
@@ -85,6 +86,7 @@ p3d::McWorkspace bind(void *base, const Layout &l) {
     ws.round_acc = reinterpret_cast<unsigned long long *>(b + l.round_acc);
     ws.round_prefix = reinterpret_cast<unsigned long long *>(b + l.round_prefix);
     ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
+    ws.tbase = reinterpret_cast<uint32_t *>(b + l.tbase);
     ws.ptab = reinterpret_cast<uint4 *>(b + l.ptab);
     ws.nf = reinterpret_cast<uint32_t *>(b + l.nf);
     ws.f8 = reinterpret_cast<unsigned long long *>(b + l.f8);
@@ -230,8 +232,8 @@ p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *worksp
     if (!make_geom(desc, &g) || !workspace || !table_out) return fail(P3D_ERR_INVALID, "p3d_mc_export_first_plane: invalid argument");
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
-    P3D_CUDA(cudaMemcpyAsync(table_out, ws.ptab, (size_t)(g.ry * g.np) * sizeof(uint4), cudaMemcpyDeviceToDevice,
-                             static_cast<cudaStream_t>(stream)));
+    p3d::launch_export_plane(table_out, g, ws, static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }
 
@@ -243,8 +245,7 @@ p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace, co
     if (delta < 0 || delta > INT32_MAX) return fail(P3D_ERR_OVERFLOW, "p3d_mc_import_halo_plane: delta out of range");
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(workspace, l);
-    p3d::launch_import_halo(ws.ptab + g.owned_x * g.ry * g.np, table_in, g.ry * g.np, static_cast<uint32_t>(delta),
-                            static_cast<cudaStream_t>(stream));
+    p3d::launch_import_halo(g, ws, table_in, static_cast<uint32_t>(delta), static_cast<cudaStream_t>(stream));
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }
