@@ -257,20 +257,36 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     // Queue state, identical in every thread:
     uint32_t q_head = 0, q_count = 0, ring_used = 0, ring_tail = 0;
 
+    // the table entries of a tile were written relative to the tile (count phase, by thread 4 * row): once its first
+    // vertex id is known the same thread makes them absolute, so the face pass needs no per-tile indirection
+    // (load issued before the tile's vertices are written, add + store after: the round trip to L2 is hidden)
+    auto table_entry = [&](const int4 &c) -> uint4 * {
+        if (mode != 0 || (tid & 3) != 0) return nullptr;
+        const int tx = c.x + (tid >> 5), ty = c.y + ((tid >> 2) & 7);
+        return (tx < ox && ty < ry) ? ws.ptab + ((int64_t)tx * ry + ty) * np + c.z : nullptr;
+    };
+    auto load_entry = [&](const uint4 *e) {
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (e) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(e) : "memory");
+        return t;
+    };
+    auto finish_entry = [&](uint4 *e, uint4 t, const int4 &c, unsigned long long base, uint32_t count) {
+        if (e) *e = make_uint4(t.x + (uint32_t)base, t.y + (uint32_t)base, t.z + (uint32_t)base, t.w);
+        if (mode == 0 && tid == 0 && (uint32_t)c.w == ntiles - 1) ws.header->total_v = base + count;
+    };
     // vertices of the pending tile in queue slot `slot`, whose first vertex id is `base`
     auto retire = [&](uint32_t slot, unsigned long long base) {
         const int4 c = S.q[slot].coord;
         const uint32_t start = S.q[slot].start, count = S.q[slot].count;
-        if (tid == 0 && mode == 0) {
-            ws.tbase[c.w] = (uint32_t)base;
-            if ((uint32_t)c.w == ntiles - 1) ws.header->total_v = base + count;
-        }
+        uint4 *const te = table_entry(c);
+        const uint4 tv = load_entry(te);
         for (uint32_t k = tid; k < count; k += kTileThreads) {
             uint32_t idx = start + k;
             if (idx >= (uint32_t)kRing) idx -= kRing;
             const unsigned long long id = base + k;
             if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
         }
+        finish_entry(te, tv, c, base, count);
         ring_used -= count;
         q_head = (q_head + 1) % kQueue;
         --q_count;
@@ -414,8 +430,8 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         }
         if (mode == 0 && tid == 0) tile_publish(ws, tile, vt, ntiles);
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
-        // table entry of my (row, piece): first ids relative to the tile + the tile, whose first id lands in tbase
-        if (mode == 0 && own && w == 0) ws.ptab[grow * np + p] = make_uint4(vx_rel, vy_rel, vz_rel, tile);
+        // table entry of my (row, piece): first ids relative to the tile; made absolute by finish_table()
+        if (mode == 0 && own && w == 0) ws.ptab[grow * np + p] = make_uint4(vx_rel, vy_rel, vz_rel, nf);
         const uint32_t first[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
         const uint32_t wmask[3] = {m0, m1, m2};
         const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
@@ -470,9 +486,9 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 retire(q_head, tb);
             }
             const unsigned long long tb = wait_base(tile);
-            if (tid == 0 && mode == 0) {
-                ws.tbase[tile] = (uint32_t)tb;
-                if (tile == ntiles - 1) ws.header->total_v = tb + vt;
+            {
+                uint4 *const te = table_entry(tc);
+                finish_entry(te, load_entry(te), tc, tb, vt);
             }
             for (uint32_t c0 = 0; c0 < vt; c0 += kRing) {
 #pragma unroll
@@ -572,26 +588,35 @@ __global__ void __launch_bounds__(256) k_fscan(McGeom g, McWorkspace ws) {
 // carries the id of the first crossing of each mask along the piece (table entry + popcounts), and
 // parks {corner words, masks, first ids} of every word with active cells in shared memory.  The sparse
 // work then runs lane-balanced: one active cell per lane (case, triangle count), one triangle per lane
-// (three ranks, 12-byte store).  Cube edge e -> entry n of a word's rank table, following the owner map of
-// :178-192:
-//   e: 0 1 2 3 4  5  6  7 8 9 10 11
-//   n: 0 3 5 1 8 10 11  9 2 4  7  6     n = q for the edges at sample z; n = 8.. for e4..e7, which sit at
-// sample z+1 of masks q0, q3, q5, q1: their entries hold {mask >> 1, first id + (mask & 1)}, so that one
-// formula  id = entry.id + popc(entry.mask & bits below z)  serves all twelve.
+// (three ranks, 12-byte store).  Cube edge e -> nibble n = q | up << 3 of a word's rank table, following the
+// owner map of :178-192:
+//   e: 0 1 2 3 4  5  6 7 8 9 10 11
+//   n: 0 3 5 1 8 11 13 9 2 4  7  6     e4..e7 are the x-/y-edges at sample z+1 (up = 1) of masks q0, q3, q5, q1
+// and one formula serves all twelve:  id = first id of mask q + popc(mask q & bits below z + up).
+// All global loads of a group are issued in one batch; the triangle counts of the NEXT group (the early-out
+// test) are fetched one iteration ahead.
 // ---------------------------------------------------------------------------------------------
-constexpr uint64_t kEdgeToEntry = (0ull << 0) | (3ull << 4) | (5ull << 8) | (1ull << 12) | (8ull << 16) | (10ull << 20) |
-                                  (11ull << 24) | (9ull << 28) | (2ull << 32) | (4ull << 36) | (7ull << 40) |
+constexpr uint64_t kEdgeToEntry = (0ull << 0) | (3ull << 4) | (5ull << 8) | (1ull << 12) | (8ull << 16) | (11ull << 20) |
+                                  (13ull << 24) | (9ull << 28) | (2ull << 32) | (4ull << 36) | (7ull << 40) |
                                   (6ull << 44);
 constexpr int kFaceWarps = 4;
-constexpr int kFacePieces = 16;    // pieces per warp iteration
+#ifndef P3D_FACE_CTAS
+#define P3D_FACE_CTAS 6
+#endif
+constexpr int kFaceCtasPerSm = P3D_FACE_CTAS;
+constexpr int kFacePieces = 16;    // pieces per warp iteration (a "group")
+#ifndef P3D_FACE_CHUNK
+#define P3D_FACE_CHUNK 8
+#endif
+constexpr int kFaceChunk = P3D_FACE_CHUNK;  // groups per ticket
 constexpr int kFaceSlots = 64;     // bit words per warp iteration
-constexpr int kCellCap = 512;
+constexpr int kCellCap = 256;
 constexpr int kTriBatch = 160;     // triangles of one batch of 32 cells (<= 5 each)
-constexpr int kRankStride = 13;    // uint2 per slot: 12 entries + 1 pad (bank spread)
+constexpr int kRankStride = 9;     // uint2 per slot: 8 entries + 1 pad (bank spread)
 
 struct FaceScratch {
     uint4 corner[kFaceSlots][2];          // per word slot: {a, b, c, d} and the words that follow them in z
-    uint2 rank[kFaceSlots * kRankStride];  // per word slot and entry n: {mask, id of its first crossing (+ vertex_id_base)}
+    uint2 rank[kFaceSlots * kRankStride];  // per word slot and mask q: {mask, id of its first crossing (+ vertex_id_base)}
     uint16_t cell[kCellCap];              // slot<<5 | bit
     uint32_t tri[kTriBatch];              // slot<<5 | bit | three entry nibbles << 12
 };
@@ -603,7 +628,7 @@ __device__ __forceinline__ uint32_t corner_code(const uint4 &w, const uint4 &n, 
            ((__funnelshift_r(w.z, n.z, i) & 3u) << 4) | ((__funnelshift_r(w.w, n.w, i) & 3u) << 6);
 }
 
-__global__ void __launch_bounds__(kFaceWarps * 32, 5)
+__global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
     k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces) {
     extern __shared__ __align__(16) unsigned char face_smem[];
     // per corner code: up to 15 entry nibbles, nibble 15 = #triangles
@@ -627,196 +652,247 @@ __global__ void __launch_bounds__(kFaceWarps * 32, 5)
     __syncthreads();
     FaceScratch &sc = s_scratch[warp];
 
-    const int np = g.np, ry = (int)g.ry, rx = (int)g.rx, rz = (int)g.rz;
+    const int np = g.np, ry = (int)g.ry, rz = (int)g.rz;
     const int64_t bstride = 4 * (int64_t)np, plane_pieces = (int64_t)ry * np;
     const int64_t ngroups = (g.npieces + kFacePieces - 1) / kFacePieces;
-    const int64_t nwarps = (int64_t)gridDim.x * kFaceWarps;
     const int h = lane & 1;  // which half of the piece
+    const uint32_t lanes_below = (1u << lane) - 1u;
 
-    for (int64_t grp = (int64_t)blockIdx.x * kFaceWarps + warp; grp < ngroups; grp += nwarps) {
-        const int64_t gi = grp * kFacePieces + (lane >> 1);
-        const bool valid = gi < g.npieces;
+    // ---- work distribution: chunks of kFaceChunk consecutive groups by ticket (the cost of a group follows the
+    // surface, so a static round-robin leaves SMs idle at the end); the ticket of the next chunk is taken a
+    // chunk ahead of its use ----
+    uint32_t ticket_ahead = 0;
+    auto take_ticket = [&]() {
+        if (lane == 0) ticket_ahead = atomicAdd(&ws.header->ticket_faces, 1u);
+    };
+    take_ticket();
+    int64_t chunk_cur = 0, chunk_end = 0;
+    bool exhausted = false;
+    auto next_group = [&]() -> int64_t {
+        if (chunk_cur == chunk_end && !exhausted) {
+            chunk_cur = (int64_t)__shfl_sync(kFull, ticket_ahead, 0) * kFaceChunk;
+            chunk_end = chunk_cur + kFaceChunk < ngroups ? chunk_cur + kFaceChunk : ngroups;
+            if (chunk_cur >= ngroups) {
+                exhausted = true;
+                chunk_cur = chunk_end = 0;
+            } else {
+                take_ticket();
+            }
+        }
+        return exhausted ? -1 : chunk_cur++;
+    };
+    auto group_counts = [&](int64_t gr) {  // triangle count of my piece of group gr
+        const int64_t i = gr * kFacePieces + (lane >> 1);
+        return (gr >= 0 && i < g.npieces) ? __ldg(ws.nf + i) : 0u;
+    };
+
+    // ---- everything a group reads from global memory, issued as one batch (a group ahead of its use) ----
+    uint4 ta, tb, td, tcc;            // table entries of my piece in rows a (x,y), b (x+1,y), d (x,y+1), c (x+1,y+1)
+    uint32_t A[3], B[3], C[3], D[3];  // my two bit words of the four rows and the word after them
+    uint32_t nax, nay, nby, ndx;      // lane 31: entries of the piece after mine (for the cell at bit 127)
+    unsigned long long fbase_ld;      // lane 0: index of the group's first face
+    int p_ld;                         // my piece index within its row
+    auto issue_loads = [&](int64_t gr, uint32_t nf) {
+        ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) A[i] = B[i] = C[i] = D[i] = 0u;
+        nax = nay = nby = ndx = 0u;
+        fbase_ld = 0;
+        p_ld = 0;
+        if (!__any_sync(kFull, nf != 0u)) return;
+        const int64_t gi = gr * kFacePieces + (lane >> 1);
         int64_t row;
-        int p, x, y;
+        int p;
         if (g.npieces <= 0x7fffffffll) {
-            const uint32_t rw = (uint32_t)gi / (uint32_t)np;
+            const uint32_t rw = np == 1 ? (uint32_t)gi : (uint32_t)__umul64hi((unsigned long long)gi, g.magic_np);
             p = (int)((uint32_t)gi - rw * (uint32_t)np);
-            x = (int)(rw / (uint32_t)ry), y = (int)(rw - (uint32_t)x * (uint32_t)ry);
             row = rw;
         } else {
             row = gi / np;
             p = (int)(gi - row * np);
-            x = (int)(row / ry), y = (int)(row - (int64_t)x * ry);
         }
-        const bool hc = valid && (x + 1 < rx) && (y + 1 < ry);
-        uint4 ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
-        // a table entry holds ids relative to its tile; .w names the tile, tbase[] its first vertex id
-        auto entry = [&](int64_t i) {
-            uint4 t = ws.ptab[i];
-            const uint32_t b = ws.tbase[t.w];
-            t.x += b, t.y += b, t.z += b;
-            return t;
-        };
-        uint32_t nf = 0;
-        if (hc) {
-            nf = ws.nf[gi];
-            ta = entry(gi);
-            tb = entry(gi + plane_pieces);
-            td = entry(gi + np);
-            tcc = entry(gi + plane_pieces + np);
-        }
-        if (!__any_sync(kFull, nf != 0u)) continue;
-
-        // entries of the next piece of the same rows: the cell at bit 127 reads its z+1 edges there
-        uint32_t nax = __shfl_down_sync(kFull, ta.x, 2), nay = __shfl_down_sync(kFull, ta.y, 2);
-        uint32_t nby = __shfl_down_sync(kFull, tb.y, 2), ndx = __shfl_down_sync(kFull, td.x, 2);
-        if (lane >= 30 && hc && p + 1 < np) {
-            const uint4 t0 = entry(gi + 1);
-            nax = t0.x, nay = t0.y;
-            nby = entry(gi + 1 + plane_pieces).y;
-            ndx = entry(gi + 1 + np).x;
-        }
-        unsigned long long fbase = 0;
-        if (lane == 0) fbase = ws.f8[grp * (kFacePieces / 8)];
-        fbase = __shfl_sync(kFull, fbase, 0);
-        const uint32_t finc = warp_incl_scan(h ? 0u : nf, lane);  // faces of the pieces up to and including mine
-
-        uint32_t actw[2] = {0, 0};
-        uint32_t nact = 0;
-        uint4 last_w = make_uint4(0, 0, 0, 0), last_n = last_w;  // corner words of the piece's last word (patch below)
-        {
-            uint32_t m[2][8];
-            uint32_t A[3] = {0, 0, 0}, B[3] = {0, 0, 0}, C[3] = {0, 0, 0}, D[3] = {0, 0, 0};
-            if (nf) {
-                const uint32_t *pa = ws.bits + row * bstride + 4 * p + 2 * h;
-                const uint32_t *pb = pa + ry * bstride, *pd = pa + bstride, *pc = pb + bstride;
-                const uint2 a2 = __ldg(reinterpret_cast<const uint2 *>(pa)), b2 = __ldg(reinterpret_cast<const uint2 *>(pb));
-                const uint2 c2 = __ldg(reinterpret_cast<const uint2 *>(pc)), d2 = __ldg(reinterpret_cast<const uint2 *>(pd));
-                const bool more = h == 0 || p + 1 < np;  // the word after mine exists in the row
-                A[0] = a2.x, A[1] = a2.y, A[2] = more ? __ldg(pa + 2) : 0u;
-                B[0] = b2.x, B[1] = b2.y, B[2] = more ? __ldg(pb + 2) : 0u;
-                C[0] = c2.x, C[1] = c2.y, C[2] = more ? __ldg(pc + 2) : 0u;
-                D[0] = d2.x, D[1] = d2.y, D[2] = more ? __ldg(pd + 2) : 0u;
+        p_ld = p;
+        // The piece after an active piece in its row is loaded too: the cell at bit 127 has its z+1 edges there.
+        const uint32_t nf_prev = __shfl_up_sync(kFull, nf, 2);
+        if (nf != 0u || (lane >= 2 && p >= 1 && nf_prev != 0u)) {
+            const uint4 *e = ws.ptab + gi;
+            ta = __ldg(e), tb = __ldg(e + plane_pieces), td = __ldg(e + np), tcc = __ldg(e + plane_pieces + np);
+            if (lane == 31 && nf && p + 1 < np) {
+                const uint4 t0 = __ldg(e + 1);
+                nax = t0.x, nay = t0.y;
+                nby = __ldg(e + 1 + plane_pieces).y;
+                ndx = __ldg(e + 1 + np).x;
             }
-            uint32_t half_lo = 0, half_hi = 0;  // crossings of my two words per mask, 8-bit fields
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
+        }
+        if (nf) {
+            const uint32_t *pa = ws.bits + row * bstride + 4 * p + 2 * h;
+            const uint32_t *pb = pa + ry * bstride, *pd = pa + bstride, *pc = pb + bstride;
+            const uint2 a2 = __ldg(reinterpret_cast<const uint2 *>(pa)), b2 = __ldg(reinterpret_cast<const uint2 *>(pb));
+            const uint2 c2 = __ldg(reinterpret_cast<const uint2 *>(pc)), d2 = __ldg(reinterpret_cast<const uint2 *>(pd));
+            const bool more = h == 0 || p + 1 < np;  // the word after mine exists in the row
+            A[0] = a2.x, A[1] = a2.y, A[2] = more ? __ldg(pa + 2) : 0u;
+            B[0] = b2.x, B[1] = b2.y, B[2] = more ? __ldg(pb + 2) : 0u;
+            C[0] = c2.x, C[1] = c2.y, C[2] = more ? __ldg(pc + 2) : 0u;
+            D[0] = d2.x, D[1] = d2.y, D[2] = more ? __ldg(pd + 2) : 0u;
+        }
+        if (lane == 0) fbase_ld = ws.f8[gr * (kFacePieces / 8)];
+    };
+
+    int64_t g0 = next_group(), g1 = next_group();
+    uint32_t nf0 = group_counts(g0), nf1 = group_counts(g1);  // != 0 only for rows with x + 1 < rx and y + 1 < ry (k_tile)
+    issue_loads(g0, nf0);
+
+    while (g0 >= 0) {
+        const int64_t g2 = next_group();
+        const uint32_t nf2 = group_counts(g2);
+        const uint32_t nf = nf0;
+        const bool active = __any_sync(kFull, nf != 0u);
+
+        // ---- dense phase: masks, first ids, scratch of the words with active cells ----
+        uint32_t actw[2] = {0u, 0u};
+        uint32_t nact = 0, cincl = 0, ncell = 0, finc = 0;
+        uint32_t xax = 0, xay = 0, xby = 0, xdx = 0;
+        unsigned long long fbase = 0;
+        if (active) {
+            // entries of the next piece of the same rows (lane 31 loaded its own)
+            {
+                const uint32_t s0 = __shfl_down_sync(kFull, ta.x, 2), s1 = __shfl_down_sync(kFull, ta.y, 2);
+                const uint32_t s2 = __shfl_down_sync(kFull, tb.y, 2), s3 = __shfl_down_sync(kFull, td.x, 2);
+                xax = lane < 30 ? s0 : nax, xay = lane < 30 ? s1 : nay, xby = lane < 30 ? s2 : nby, xdx = lane < 30 ? s3 : ndx;
+            }
+            fbase = __shfl_sync(kFull, fbase_ld, 0);
+            finc = warp_incl_scan(h ? 0u : nf, lane);  // faces of the pieces up to and including mine
+
+            // the eight masks of my word w (samples outside the grid were staged as 0.0f in every row, so the x/y
+            // masks are zero there, and a z crossing cut by zv can only sit above every valid cell of the row)
+            auto masks = [&](int w, uint32_t (&m)[8], uint32_t &act) {
                 const uint32_t A2 = __funnelshift_r(A[w], A[w + 1], 1), B2 = __funnelshift_r(B[w], B[w + 1], 1);
                 const uint32_t C2 = __funnelshift_r(C[w], C[w + 1], 1), D2 = __funnelshift_r(D[w], D[w + 1], 1);
-                const uint32_t zv = low_mask(rz - 1 - (p * kTileZ + 32 * (2 * h + w)));
-                // samples outside the grid were staged as 0.0f in every row, so the x/y masks are zero there, and a
-                // z crossing cut by zv can only sit above every valid cell of the row
-                m[w][0] = A[w] ^ B[w], m[w][1] = A[w] ^ D[w], m[w][2] = (A[w] ^ A2) & zv, m[w][3] = B[w] ^ C[w];
-                m[w][4] = (B[w] ^ B2) & zv, m[w][5] = D[w] ^ C[w], m[w][6] = (D[w] ^ D2) & zv, m[w][7] = (C[w] ^ C2) & zv;
+                const uint32_t zv = low_mask(rz - 1 - (p_ld * kTileZ + 32 * (2 * h + w)));
+                m[0] = A[w] ^ B[w], m[1] = A[w] ^ D[w], m[2] = (A[w] ^ A2) & zv, m[3] = B[w] ^ C[w];
+                m[4] = (B[w] ^ B2) & zv, m[5] = D[w] ^ C[w], m[6] = (D[w] ^ D2) & zv, m[7] = (C[w] ^ C2) & zv;
                 const uint32_t any = A[w] | B[w] | C[w] | D[w] | A2 | B2 | C2 | D2;
                 const uint32_t all = A[w] & B[w] & C[w] & D[w] & A2 & B2 & C2 & D2;
-                actw[w] = nf ? ((any & ~all) & zv) : 0u;  // :154,168-176
-                nact += __popc(actw[w]);
-                half_lo += (uint32_t)__popc(m[w][0]) | ((uint32_t)__popc(m[w][1]) << 8) | ((uint32_t)__popc(m[w][2]) << 16) |
-                           ((uint32_t)__popc(m[w][3]) << 24);
-                half_hi += (uint32_t)__popc(m[w][4]) | ((uint32_t)__popc(m[w][5]) << 8) | ((uint32_t)__popc(m[w][6]) << 16) |
-                           ((uint32_t)__popc(m[w][7]) << 24);
-            }
-            // first ids at my first word: the table entry, plus the first half's crossings for the second half
-            const uint32_t prev_lo = __shfl_up_sync(kFull, half_lo, 1), prev_hi = __shfl_up_sync(kFull, half_hi, 1);
+                act = nf ? ((any & ~all) & zv) : 0u;  // :154,168-176
+            };
             uint32_t run[8] = {ta.x, ta.y, ta.z, tb.y, tb.z, td.x, td.z, tcc.z};
+            // crossings of the first half's two words per mask (8-bit fields): the second half starts after them
+            uint32_t half_lo = 0, half_hi = 0;
+            uint32_t m0[8], m1[8];
+            masks(0, m0, actw[0]);
+            masks(1, m1, actw[1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                half_lo += (uint32_t)(__popc(m0[q]) + __popc(m1[q])) << (8 * q);
+                half_hi += (uint32_t)(__popc(m0[q + 4]) + __popc(m1[q + 4])) << (8 * q);
+            }
+            const uint32_t prev_lo = __shfl_up_sync(kFull, half_lo, 1), prev_hi = __shfl_up_sync(kFull, half_hi, 1);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const uint32_t prev = ((q < 4 ? prev_lo : prev_hi) >> (8 * (q & 3))) & 255u;
                 run[q] += (uint32_t)vbase + (h ? prev : 0u);
             }
+            if (actw[0]) {
+                const int slot = lane * 2;
+                sc.corner[slot][0] = make_uint4(A[0], B[0], C[0], D[0]);
+                sc.corner[slot][1] = make_uint4(A[1], B[1], C[1], D[1]);
+                uint2 *rk = &sc.rank[slot * kRankStride];
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                if (actw[w]) {
-                    const int slot = lane * 2 + w;
-                    sc.corner[slot][0] = make_uint4(A[w], B[w], C[w], D[w]);
-                    sc.corner[slot][1] = make_uint4(A[w + 1], B[w + 1], C[w + 1], D[w + 1]);
-                    uint2 *rk = &sc.rank[slot * kRankStride];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) rk[q] = make_uint2(m[w][q], run[q]);
-                    // e4..e7: the crossing at sample z+1 of masks q0, q1, q3, q5
-                    rk[8] = make_uint2(m[w][0] >> 1, run[0] + (m[w][0] & 1u));
-                    rk[9] = make_uint2(m[w][1] >> 1, run[1] + (m[w][1] & 1u));
-                    rk[10] = make_uint2(m[w][3] >> 1, run[3] + (m[w][3] & 1u));
-                    rk[11] = make_uint2(m[w][5] >> 1, run[5] + (m[w][5] & 1u));
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) run[q] += __popc(m[w][q]);
+                for (int q = 0; q < 8; ++q) rk[q] = make_uint2(m0[q], run[q]);
             }
-            if (h) {
-                last_w = make_uint4(A[1], B[1], C[1], D[1]);
-                last_n = make_uint4(A[2], B[2], C[2], D[2]);
+            if (actw[1]) {
+                const int slot = lane * 2 + 1;
+                sc.corner[slot][0] = make_uint4(A[1], B[1], C[1], D[1]);
+                sc.corner[slot][1] = make_uint4(A[2], B[2], C[2], D[2]);
+                uint2 *rk = &sc.rank[slot * kRankStride];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rk[q] = make_uint2(m1[q], run[q] + __popc(m0[q]));
             }
+            nact = __popc(actw[0]) + __popc(actw[1]);
+            cincl = warp_incl_scan(nact, lane);
+            ncell = __shfl_sync(kFull, cincl, 31);
         }
-        const uint32_t cincl = warp_incl_scan(nact, lane);
-        const uint32_t ncell = __shfl_sync(kFull, cincl, 31);
-        unsigned long long frun = fbase;
+
+        // ---- the next group's loads fly while this group's sparse phase runs from shared memory ----
+        issue_loads(g1, nf1);
         __syncwarp();
 
-        for (uint32_t c0 = 0; c0 < ncell; c0 += kCellCap) {
-            {
-                uint32_t pos = cincl - nact - c0;  // wraps below the chunk: filtered by the range test
+        if (active) {
+            unsigned long long frun = fbase;
+            for (uint32_t c0 = 0; c0 < ncell; c0 += kCellCap) {
+                {
+                    uint32_t pos = cincl - nact - c0;  // wraps below the chunk: filtered by the range test
 #pragma unroll
-                for (int w = 0; w < 2; ++w)
-                    for (uint32_t rem = actw[w]; rem; ++pos) {
-                        const int i = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        if (pos < (uint32_t)kCellCap) sc.cell[pos] = (uint16_t)(((lane * 2 + w) << 5) | i);
+                    for (int w = 0; w < 2; ++w)
+                        for (uint32_t rem = actw[w]; rem; ++pos) {
+                            const int i = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            if (pos < (uint32_t)kCellCap) sc.cell[pos] = (uint16_t)(((lane * 2 + w) << 5) | i);
+                        }
+                }
+                __syncwarp();
+                const uint32_t n = ncell - c0 < (uint32_t)kCellCap ? ncell - c0 : (uint32_t)kCellCap;
+                for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+                    // one cell per lane: case, triangle count, and one list entry per triangle
+                    const uint32_t k = k0 + lane;
+                    uint32_t nt = 0, e = 0;
+                    uint64_t tt = 0;
+                    if (k < n) {
+                        e = sc.cell[k];
+                        tt = s_table[corner_code(sc.corner[e >> 5][0], sc.corner[e >> 5][1], e & 31u)];
+                        nt = (uint32_t)(tt >> 60);
+                    }
+                    // exclusive prefix of nt (<= 5: three bit planes) by ballots: no shuffle chain
+                    const uint32_t b0 = __ballot_sync(kFull, nt & 1u), b1 = __ballot_sync(kFull, nt & 2u), b2 = __ballot_sync(kFull, nt & 4u);
+                    const uint32_t tp = __popc(b0 & lanes_below) + 2u * __popc(b1 & lanes_below) + 4u * __popc(b2 & lanes_below);
+                    const uint32_t btot = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+                    {
+                        const uint32_t lo = (uint32_t)tt, hi = (uint32_t)(tt >> 32);
+                        uint32_t *dst = &sc.tri[tp];
+                        if (nt > 0) dst[0] = e | ((lo & 0xfffu) << 12);
+                        if (nt > 1) dst[1] = e | (((lo >> 12) & 0xfffu) << 12);
+                        if (nt > 2) dst[2] = e | ((__funnelshift_r(lo, hi, 24) & 0xfffu) << 12);
+                        if (nt > 3) dst[3] = e | (((hi >> 4) & 0xfffu) << 12);
+                        if (nt > 4) dst[4] = e | (((hi >> 16) & 0xfffu) << 12);
+                    }
+                    __syncwarp();
+                    // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
+                    int32_t *const out0 = faces + frun * 3ull;
+                    for (uint32_t j = lane; j < btot; j += 32) {
+                        const uint32_t ent = sc.tri[j];
+                        const uint32_t i = ent & 31u;
+                        const uint32_t below0 = (1u << i) - 1u, below1 = (2u << i) - 1u;  // bits below z / below z+1
+                        const uint2 *rk = &sc.rank[((ent >> 5) & 63u) * kRankStride];
+                        int32_t *out = out0 + j * 3u;
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const uint32_t nib = ent >> (12 + 4 * cc);
+                            const uint2 en = rk[nib & 7u];
+                            out[cc] = (int32_t)(en.y + __popc(en.x & ((nib & 8u) ? below1 : below0)));
+                        }
+                    }
+                    __syncwarp();
+                    frun += btot;
+                }
+            }
+
+            // the last cell of a piece (bit 127) has its z+1 x-/y-edges in the NEXT piece, which is numbered by
+            // another tile: overwrite those indices with that piece's table entries (its bit 0 is rank 0)
+            if (h && (actw[1] >> 31)) {
+                const int slot = lane * 2 + 1;
+                uint64_t tt = s_table[corner_code(sc.corner[slot][0], sc.corner[slot][1], 31)];
+                const uint32_t nt = (uint32_t)(tt >> 60);
+                int32_t *out = faces + (fbase + finc - nt) * 3ull;
+                for (uint32_t t = 0; t < nt; ++t)
+                    for (int cc = 0; cc < 3; ++cc, tt >>= 4) {
+                        const uint32_t n = (uint32_t)tt & 15u;
+                        if (n >= 8u) out[t * 3 + cc] = vbase + (int32_t)(n == 8u ? xax : (n == 9u ? xay : (n == 11u ? xby : xdx)));
                     }
             }
             __syncwarp();
-            const uint32_t n = ncell - c0 < (uint32_t)kCellCap ? ncell - c0 : (uint32_t)kCellCap;
-            for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-                // one cell per lane: case, triangle count, and one list entry per triangle
-                const uint32_t k = k0 + lane;
-                uint32_t nt = 0, e = 0;
-                uint64_t tt = 0;
-                if (k < n) {
-                    e = sc.cell[k];
-                    tt = s_table[corner_code(sc.corner[e >> 5][0], sc.corner[e >> 5][1], e & 31u)];
-                    nt = (uint32_t)(tt >> 60);
-                }
-                const uint32_t tincl = warp_incl_scan(nt, lane);
-                const uint32_t btot = __shfl_sync(kFull, tincl, 31);
-                uint32_t tp = tincl - nt;
-                uint32_t lo = (uint32_t)tt, hi = (uint32_t)(tt >> 32);
-                for (uint32_t t = 0; t < nt; ++t) {
-                    sc.tri[tp++] = e | ((lo & 0xfffu) << 12);
-                    lo = __funnelshift_r(lo, hi, 12);
-                    hi >>= 12;
-                }
-                __syncwarp();
-                // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
-                for (uint32_t j = lane; j < btot; j += 32) {
-                    const uint32_t ent = sc.tri[j];
-                    const uint32_t i = ent & 31u;
-                    const uint32_t lt = (1u << i) - 1u;
-                    const uint2 *rk = &sc.rank[((ent >> 5) & 63u) * kRankStride];
-                    int32_t *out = faces + (frun + j) * 3ull;
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        const uint2 en = rk[(ent >> (12 + 4 * cc)) & 15u];
-                        out[cc] = (int32_t)(en.y + __popc(en.x & lt));  // crossings of the mask below the edge's sample
-                    }
-                }
-                __syncwarp();
-                frun += btot;
-            }
         }
-
-        // the last cell of a piece (bit 127) has its z+1 x-/y-edges in the NEXT piece, which is numbered by
-        // another tile: overwrite those indices with that piece's table entries (its bit 0 is rank 0)
-        if (h && (actw[1] >> 31)) {
-            uint64_t tt = s_table[corner_code(last_w, last_n, 31)];
-            const uint32_t nt = (uint32_t)(tt >> 60);
-            int32_t *out = faces + (fbase + finc - nt) * 3ull;
-            for (uint32_t t = 0; t < nt; ++t)
-                for (int cc = 0; cc < 3; ++cc, tt >>= 4) {
-                    const uint32_t n = (uint32_t)tt & 15u;
-                    if (n >= 8u) out[t * 3 + cc] = vbase + (int32_t)(n == 8u ? nax : (n == 9u ? nay : (n == 10u ? nby : ndx)));
-                }
-        }
-        __syncwarp();
+        g0 = g1, nf0 = nf1;
+        g1 = g2, nf1 = nf2;
     }
 }
 
@@ -918,46 +994,36 @@ void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s) {
     if (g.npieces <= 0) return;
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
-    const int64_t want = (groups + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * 5;
+    const int64_t want = ((groups + kFaceChunk - 1) / kFaceChunk + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * kFaceCtasPerSm;
     static const bool attr = [] {
         cudaFuncSetAttribute(k_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaceSmemBytes);
         return true;
     }();
     (void)attr;
+    cudaMemsetAsync(&ws.header->ticket_faces, 0, sizeof(unsigned int), s);
     k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces);
 }
 
-// Multi-GPU.  Export: the first plane's table entries with absolute (shard-local) ids.  Import: install the next
-// shard's first-plane entries, shifted by this shard's vertex count, as this shard's halo-plane numbering; they
-// name the extra tile slot `ntiles`, whose tbase stays 0.
-__global__ void k_export_plane(uint4 *__restrict__ dst, const uint4 *__restrict__ ptab, const uint32_t *__restrict__ tbase, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const uint4 t = ptab[i];
-        const uint32_t b = tbase[t.w];
-        dst[i] = make_uint4(t.x + b, t.y + b, t.z + b, 0u);
-    }
-}
-
-__global__ void k_import_halo(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, uint32_t delta, uint32_t slot) {
+// Multi-GPU.  Export: the first plane's table entries (shard-local ids).  Import: install the next shard's
+// first-plane entries, shifted by this shard's vertex count, as this shard's halo-plane numbering.
+__global__ void k_shift_plane(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, uint32_t delta) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const uint4 t = src[i];
-        dst[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, slot);
+        dst[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, 0u);
     }
 }
 
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
     const int64_t n = g.ry * (int64_t)g.np;
     if (n <= 0) return;
-    k_export_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(table_out), ws.ptab, ws.tbase, n);
+    k_shift_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(table_out), ws.ptab, n, 0u);
 }
 
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s) {
     const int64_t n = g.ry * (int64_t)g.np;
     if (n <= 0) return;
-    k_import_halo<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.ptab + g.owned_x * n, reinterpret_cast<const uint4 *>(table_in), n,
-                                                              delta, (uint32_t)g.ntiles);
+    k_shift_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.ptab + g.owned_x * n, reinterpret_cast<const uint4 *>(table_in), n, delta);
 }
 
 }  // namespace p3d

@@ -48,6 +48,7 @@ struct McGeom {
     int64_t npieces;      // owned_x * ry * np
     int64_t nscan;        // ceil(npieces / kFscanTile)
     int64_t nrounds;      // ceil(ntiles / 256): rounds of the tile scan
+    uint64_t magic_np;    // floor(2^64 / np) + 1: n / np == umul64hi(n, magic_np) for n < 2^32 (np > 1)
 };
 
 // Workspace header (device).  Zeroed before every count.
@@ -56,7 +57,8 @@ struct McHeader {
     unsigned long long total_f;
     unsigned int ticket;       // dynamic tile id of k_tile
     unsigned int ticket_scan;  // dynamic tile id of k_fscan
-    unsigned int pad[2];
+    unsigned int ticket_faces; // dynamic chunk id of k_faces (reset by launch_faces)
+    unsigned int pad[1];
 };
 
 struct McWorkspace {
@@ -65,9 +67,8 @@ struct McWorkspace {
     unsigned long long *round_acc;     // [nrounds] arrivals<<48 | vertex count of each round of 256 tiles
     unsigned long long *round_prefix;  // [nrounds + 1] published exclusive vertex prefix of each round
     unsigned long long *status_f;  // [nscan]  look-back status words of k_fscan
-    uint32_t *tbase;               // [ntiles + 1] first vertex id of each tile (slot ntiles: imported halo entries, 0)
-    uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, tile}: first ids of the piece's x/y/z-edge vertices relative to
-                                   // its tile, and the tile
+    uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: ids of the piece's first x-/y-/z-edge vertex (relative to
+                                   // the tile until the tile's first id is known, absolute after the tile pass)
     uint32_t *nf;                  // [npieces] triangles per piece (input of k_fscan)
     unsigned long long *f8;        // [ceil(npieces/8)] index of the first face of pieces 8i..
     uint32_t *bits;                // [rx*ry][4*np] inside bits, 32 samples per word

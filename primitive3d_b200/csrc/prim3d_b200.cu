@@ -51,12 +51,13 @@ bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
     g->npieces = d->owned_x * d->ry * g->np;
     g->nscan = (g->npieces + p3d::kFscanTile - 1) / p3d::kFscanTile;
     g->nrounds = (g->ntiles + 255) / 256;
+    g->magic_np = g->np > 1 ? ~0ull / (uint64_t)g->np + 1 : 0;
     if (g->ntiles > ((int64_t)1 << 31) || d->rx * d->ry * (int64_t)g->np > ((int64_t)1 << 40)) return false;
     return true;
 }
 
 struct Layout {
-    size_t header, status, round_acc, round_prefix, status_f, tbase, zero_end, ptab, nf, f8, bits, total;
+    size_t header, status, round_acc, round_prefix, status_f, zero_end, ptab, nf, f8, bits, total;
 };
 
 Layout make_layout(const p3d::McGeom &g) {
@@ -68,7 +69,6 @@ Layout make_layout(const p3d::McGeom &g) {
     l.round_acc = off;    off += align_up((size_t)g.nrounds * 8);
     l.round_prefix = off; off += align_up((size_t)(g.nrounds + 1) * 8);
     l.status_f = off; off += align_up((size_t)g.nscan * 8);
-    l.tbase = off;    off += align_up(((size_t)g.ntiles + 1) * 4);
     l.zero_end = off;  // everything above is zeroed before a count
     l.ptab = off;     off += align_up(all_pieces * sizeof(uint4));
     l.nf = off;       off += align_up((size_t)g.npieces * 4 + 32);
@@ -86,7 +86,6 @@ p3d::McWorkspace bind(void *base, const Layout &l) {
     ws.round_acc = reinterpret_cast<unsigned long long *>(b + l.round_acc);
     ws.round_prefix = reinterpret_cast<unsigned long long *>(b + l.round_prefix);
     ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
-    ws.tbase = reinterpret_cast<uint32_t *>(b + l.tbase);
     ws.ptab = reinterpret_cast<uint4 *>(b + l.ptab);
     ws.nf = reinterpret_cast<uint32_t *>(b + l.nf);
     ws.f8 = reinterpret_cast<unsigned long long *>(b + l.f8);
