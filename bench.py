@@ -3,8 +3,8 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one full extraction (tile pass: classify + count + look-back + vertices -> face-count
-scan -> {V,F} readback -> face allocation -> faces) of a synthetic gyroid SDF
+One "step" = one full extraction (tile pass: classify + count + look-back + vertices -> {V,F}
+readback -> face allocation -> face pass: chunk scan + faces) of a synthetic gyroid SDF
 that is already resident in HBM.
 
   N = 1   gyroid 1024^3 fp32, BASELINE.json configs[2] (the HBM-roofline case)
@@ -198,7 +198,7 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     torch.cuda.synchronize()
 
-    launches_per_step = 3 + (1 if world > 1 and rank + 1 < world else 0)  # k_tile, k_fscan, k_faces (+halo import)
+    launches_per_step = 2 + (1 if world > 1 and rank + 1 < world else 0)  # k_tile, k_faces (+halo import)
 
     def step():
         return sharded.marching_cubes_slab(slab, 0.0, x0, n)
@@ -310,14 +310,13 @@ def main():
     emit_faces = lambda: capi.check(L.p3d_mc_faces(ctypes.byref(desc), ws.data_ptr(), faces.data_ptr(), 0, stream))
     nvox = slab.numel()
     k_ms = {"tile_pass": time_kernel(lambda: stage(1), before=lambda: stage(0))}
-    k_ms["face_scan"] = time_kernel(lambda: stage(2), before=lambda: stage(0))
-    stage(0), stage(1), stage(2)   # a consistent workspace for the face pass
+    stage(0), stage(1)   # a consistent workspace for the face pass
     k_ms["faces"] = time_kernel(emit_faces)
-    k_bytes = {"tile_pass": 4 * nvox + 12 * V, "face_scan": 0, "faces": 12 * F}
+    k_bytes = {"tile_pass": 4 * nvox + 12 * V, "faces": 12 * F}
     kernels = {k: {"ms": k_ms[k], "algorithmic_bytes": k_bytes[k], "achieved_gbs": k_bytes[k] / (k_ms[k] * 1e-3) / 1e9,
                    "share_of_step": k_ms[k] / sum(k_ms.values())} for k in k_ms}
     dom = max(k_ms, key=k_ms.get)
-    line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "face_scan": "k_fscan", "faces": "k_faces"}[dom],
+    line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "faces": "k_faces"}[dom],
                         "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": k_bytes[dom], "launch_ms": k_ms[dom]}

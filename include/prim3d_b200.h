@@ -114,7 +114,7 @@ p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t 
 
 /* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
  * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: tile pass (classify,
- * count, look-back, vertices), 2: face-count scan.  The face stage is p3d_mc_faces itself. */
+ * count, look-back, vertices).  The face stage (scan over chunks + faces) is p3d_mc_faces itself. */
 p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage,
                               float *vertices, int64_t vertex_capacity, void *stream);
 

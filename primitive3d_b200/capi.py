@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprim3d_b200.so")
+# P3D_CORE_LIB: tuning runs (tools/variants.py) point the ctypes view at another build of the same library
+LIB_PATH = os.environ.get("P3D_CORE_LIB") or os.path.join(_HERE, "libprim3d_b200.so")
 _lib = None
 
 P3D_OK, P3D_ERR_INVALID, P3D_ERR_CUDA, P3D_ERR_OVERFLOW, P3D_ERR_WORKSPACE = range(5)

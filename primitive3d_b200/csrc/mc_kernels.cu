@@ -10,6 +10,16 @@
 #include "mc_case_table.h"
 #include "scan_utils.cuh"
 
+#ifndef P3D_VERT_COMP
+#define P3D_VERT_COMP 0
+#endif
+#ifndef P3D_TILE_PREFETCH
+#define P3D_TILE_PREFETCH 0
+#endif
+#ifndef P3D_FACE_IDX
+#define P3D_FACE_IDX 0
+#endif
+
 namespace p3d {
 
 // Bourke case table, one packed word per case (nibble i = i-th edge index, nibble 15 =
@@ -56,19 +66,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// L2 prefetch of the same box (no shared-memory destination, no completion tracking).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
-// First vertex id of a tile: a two-level single-pass scan over tiles (no CUB / thrust).
+// Two-level single-pass scan (no CUB / thrust), used for the first vertex id of a tile (k_tile) and the
+// first face index of a chunk (k_faces).
 //
-// Tiles are grouped into rounds of 256 consecutive ids.  A tile publishes its vertex count in its
-// status word and adds it to its round's accumulator; whichever tile completes a round (the 256th
-// arrival) publishes the exclusive prefix of the NEXT round.  A tile's first id is then
-//     prefix[round] + sum of the status words of the tiles before it in its round
-// -- one batch of <= 8 independent loads per lane, however many tiles are in flight (with ~600
-// resident tiles a classic 32-wide look-back walks ~20 dependent windows).  Every wait is on a tile
-// with a smaller id; ids are handed out in increasing order to running CTAs, so the waits end.
-// The result does not depend on arrival order: numbering is deterministic.
+// Items are grouped into rounds of 256 consecutive ids.  An item publishes its count in its status
+// word and adds it to its round's accumulator; whichever item completes a round (the 256th arrival)
+// publishes the exclusive prefix of the NEXT round.  An item's exclusive prefix is then
+//     prefix[round] + sum of the status words of the items before it in its round
+// -- one batch of <= 8 independent loads per lane, however many items are in flight (with ~600
+// resident tiles a classic 32-wide look-back walks ~20 dependent windows).  Every wait is on an item
+// with a smaller id; ids are handed out in increasing order to running CTAs / warps, which publish
+// without waiting for anyone, so the waits end.  The result does not depend on arrival order:
+// numbering is deterministic.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kRoundTiles = 256;
 constexpr unsigned long long kPublished = 1ull << 63;
 constexpr unsigned long long kRoundSumMask = (1ull << 48) - 1;
 
@@ -79,33 +97,33 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
 
-// Lane 0 of the warp that owns `tile`: publish its vertex count.
-__device__ __forceinline__ void tile_publish(const McWorkspace &ws, uint32_t tile, uint32_t count, uint32_t ntiles) {
-    const uint32_t k = tile / kRoundTiles;
-    st_status(ws.status + tile, kPublished | count);
-    const uint32_t left = ntiles - k * kRoundTiles, members = left < kRoundTiles ? left : kRoundTiles;
-    const unsigned long long old = atomicAdd(ws.round_acc + k, (1ull << 48) | count);
-    if ((uint32_t)(old >> 48) == members - 1) {  // this tile completes round k
+// One lane of the owner of `item`: publish its count (< 2^39, so that a round's sum stays below 2^48).
+__device__ __forceinline__ void scan_publish(const McScan &sc, uint32_t item, unsigned long long count, uint32_t nitems) {
+    const uint32_t k = item / kRoundTiles;
+    st_status(sc.status + item, kPublished | count);
+    const uint32_t left = nitems - k * kRoundTiles, members = left < (uint32_t)kRoundTiles ? left : (uint32_t)kRoundTiles;
+    const unsigned long long old = atomicAdd(sc.round_acc + k, (1ull << 48) | count);
+    if ((uint32_t)(old >> 48) == members - 1) {  // this item completes round k
         unsigned long long base = kPublished;
-        if (k) do base = ld_status(ws.round_prefix + k); while (!(base & kPublished));
-        st_status(ws.round_prefix + k + 1, base + (old & kRoundSumMask) + count);
+        if (k) do base = ld_status(sc.round_prefix + k); while (!(base & kPublished));
+        st_status(sc.round_prefix + k + 1, base + (old & kRoundSumMask) + count);
     }
 }
 
-// One full warp: first vertex id of `tile`.  Blocking: waits for the tiles before it in its round and for the
+// One full warp: exclusive prefix of `item`.  Blocking: waits for the items before it in its round and for the
 // round's prefix.  Non-blocking: returns false if any of them is not published yet.  Also valid as a pure
 // re-read after the scan has completed (vertices-only pass).
 template <bool BLOCK>
-__device__ __forceinline__ bool tile_first_vertex(const McWorkspace &ws, uint32_t tile, int lane, unsigned long long &first) {
-    const uint32_t k = tile / kRoundTiles, j = tile % kRoundTiles;
+__device__ __forceinline__ bool scan_prefix(const McScan &sc, uint32_t item, int lane, unsigned long long &first) {
+    const uint32_t k = item / kRoundTiles, j = item % kRoundTiles;
     unsigned long long s[kRoundTiles / 32];
-    const unsigned long long *st = ws.status + (tile - j);
+    const unsigned long long *st = sc.status + (item - j);
 #pragma unroll
     for (int i = 0; i < (int)kRoundTiles / 32; ++i) s[i] = (uint32_t)(lane + 32 * i) < j ? ld_status(st + lane + 32 * i) : kPublished;
     unsigned long long acc = kPublished, ready = kPublished;
     if (lane == 0 && k) {
-        acc = ld_status(ws.round_prefix + k);
-        if (BLOCK) while (!(acc & kPublished)) acc = ld_status(ws.round_prefix + k);
+        acc = ld_status(sc.round_prefix + k);
+        if (BLOCK) while (!(acc & kPublished)) acc = ld_status(sc.round_prefix + k);
         ready = acc;
     }
 #pragma unroll
@@ -151,6 +169,7 @@ struct PendingTile {
 struct TileSmem {
     uint32_t sbits[kBoxRows * kSbitsStride];
     uint32_t piece[kTileX * kTileY];
+    uint16_t nfp[kTileX * kTileY];  // triangles of each owned (row, piece)
     float dt[kRing];       // pending vertices: interpolation parameter ...
     uint16_t ent[kRing];   // ... and edge (axis<<13 | row<<7 | z)
     uint8_t ntri[256];     // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
@@ -162,6 +181,7 @@ struct TileSmem {
     int4 coord[2];         // {x0, y0, piece, tile} of the tile of iteration it, by parity
 };
 constexpr int kTileSmemBytes = kStageBytes + (int)sizeof(TileSmem) + 128;
+static_assert(4 * (kTileSmemBytes + 1024) <= 228 * 1024, "k_tile is tuned for four CTAs per SM");
 
 template <bool TMA>
 __global__ void __launch_bounds__(kTileThreads, 4)
@@ -280,12 +300,36 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t start = S.q[slot].start, count = S.q[slot].count;
         uint4 *const te = table_entry(c);
         const uint4 tv = load_entry(te);
+#if P3D_VERT_COMP
+        // a lane per output float: consecutive lanes write consecutive words (12-byte vertices would make every
+        // store instruction touch three times the sectors it fills)
+        {
+            const int z0 = c.z * kTileZ;
+            float *const out = verts + base * 3ull;
+            for (uint32_t k = tid; k < 3u * count; k += kTileThreads) {
+                const uint32_t v = (k * 0xAAABu) >> 17, cc = k - 3u * v;  // k / 3, k % 3 (k < 2^16)
+                uint32_t idx = start + v;
+                if (idx >= (uint32_t)kRing) idx -= kRing;
+                if (base + v < vcap) {
+                    const uint32_t ent = S.ent[idx];
+                    const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
+                    const int ip = cc == 0 ? xg0 + c.x + (int)(er >> 3) : (cc == 1 ? c.y + (int)(er & 7u) : z0 + (int)ez);
+                    float pp = (float)ip;  // static_cast<float>(x), :107
+                    if (ax == cc) pp = __fadd_rn(pp, S.dt[idx]);
+                    const float sc = cc == 0 ? prm.scale[0] : (cc == 1 ? prm.scale[1] : prm.scale[2]);
+                    const float of = cc == 0 ? prm.offset[0] : (cc == 1 ? prm.offset[1] : prm.offset[2]);
+                    out[k] = __fadd_rn(__fmul_rn(pp, sc), of);  // two separately rounded ops (:298)
+                }
+            }
+        }
+#else
         for (uint32_t k = tid; k < count; k += kTileThreads) {
             uint32_t idx = start + k;
             if (idx >= (uint32_t)kRing) idx -= kRing;
             const unsigned long long id = base + k;
             if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
         }
+#endif
         finish_entry(te, tv, c, base, count);
         ring_used -= count;
         q_head = (q_head + 1) % kQueue;
@@ -295,7 +339,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     auto wait_base = [&](uint32_t t) {
         if (warp == 0) {
             unsigned long long tb = 0;
-            tile_first_vertex<true>(ws, t, lane, tb);
+            scan_prefix<true>(ws.vscan, t, lane, tb);
             if (lane == 0) S.base_wait = tb;
         }
         __syncthreads();
@@ -320,7 +364,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // trip to L2 hides behind the TMA wait.  Non-blocking.
         if (q_count && warp == 0) {
             unsigned long long tb = 0;
-            const bool ok = tile_first_vertex<false>(ws, (uint32_t)S.q[q_head].coord.w, lane, tb);
+            const bool ok = scan_prefix<false>(ws.vscan, (uint32_t)S.q[q_head].coord.w, lane, tb);
             if (lane == 0) {
                 S.base_ok = ok ? 1u : 0u;
                 S.base = tb;
@@ -361,6 +405,15 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             }
         }
         __syncthreads();  // [bits]
+#if P3D_TILE_PREFETCH
+        // the next tile's box is pulled into L2 now, so that the TMA load issued when the stage is free lands fast
+        int4 nc = make_int4(0, 0, 0, 0);
+        if (tid == 32) {
+            nc = locate(next_tile);
+            S.coord[(it + 1u) & 1u] = nc;
+            if (TMA && (uint32_t)nc.w < ntiles) tma_prefetch_3d(&tmap, nc.z * kTileZ, nc.y, nc.x);
+        }
+#endif
 
         // ---- phase 2: crossing masks and counts of my word ----
         const int x = x0 + xi, y = y0 + yi;
@@ -400,7 +453,10 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t exw = inc - cnt;
         nf += __shfl_xor_sync(kFull, nf, 1);
         nf += __shfl_xor_sync(kFull, nf, 2);
-        if (w == 0) S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
+        if (w == 0) {
+            S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
+            S.nfp[r] = (uint16_t)nf;  // <= 640
+        }
 
         const int64_t grow = (int64_t)x * ry + y;  // my row of the grid
         if (mode == 0) {
@@ -428,7 +484,35 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             wbase = __shfl_sync(kFull, e0, 4 * warp);
             wcount = __shfl_sync(kFull, seg, 4 * warp);
         }
-        if (mode == 0 && tid == 0) tile_publish(ws, tile, vt, ntiles);
+        // face offsets of the face pass: triangle counts summed per chunk of 128 consecutive (row, piece) pairs.
+        // Warp 0, a lane per x-row of the tile (its 8 rows are one RED when they fall into one chunk).
+        if (mode == 0 && warp == 7) {
+            const uint32_t v2 = *reinterpret_cast<const uint32_t *>(&S.nfp[2 * lane]);
+            uint32_t t = (v2 & 0xffffu) + (v2 >> 16);
+            t += __shfl_xor_sync(kFull, t, 1);
+            t += __shfl_xor_sync(kFull, t, 2);  // triangles of x-row lane >> 2
+            uint32_t tile_nf = t;
+            tile_nf += __shfl_xor_sync(kFull, tile_nf, 4);
+            tile_nf += __shfl_xor_sync(kFull, tile_nf, 8);
+            tile_nf += __shfl_xor_sync(kFull, tile_nf, 16);
+            if (lane == 0 && tile_nf) atomicAdd(&ws.header->total_f, (unsigned long long)tile_nf);  // F = sum of the table-row lengths, :66
+            if ((lane & 3) == 0 && t) {
+                constexpr int64_t kChunkPieces = kFacePieces * kFaceChunk;
+                const int xr = lane >> 2, ylast = (y0 + kTileY <= ry ? y0 + kTileY : ry) - 1;
+                const int64_t gfirst = ((int64_t)(x0 + xr) * ry + y0) * np + p, glast = ((int64_t)(x0 + xr) * ry + ylast) * np + p;
+                if (gfirst / kChunkPieces == glast / kChunkPieces) {
+                    atomicAdd(ws.chunk_sum + gfirst / kChunkPieces, t);
+                } else {
+                    for (int k = 0; k < kTileY; ++k) {
+                        const uint32_t nk = S.nfp[xr * kTileY + k];
+                        if (nk) atomicAdd(ws.chunk_sum + (gfirst + (int64_t)k * np) / kChunkPieces, nk);
+                    }
+                }
+            }
+        }
+        if (mode == 0 && tid == 0) {
+            scan_publish(ws.vscan, tile, vt, ntiles);
+        }
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
         // table entry of my (row, piece): first ids relative to the tile; made absolute by finish_table()
         if (mode == 0 && own && w == 0) ws.ptab[grow * np + p] = make_uint4(vx_rel, vy_rel, vz_rel, nf);
@@ -512,11 +596,13 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             ring_tail = 0;
         }
         // the next tile's coordinates are published before the barrier, its load is issued after it
+#if !P3D_TILE_PREFETCH
         int4 nc = make_int4(0, 0, 0, 0);
         if (tid == 32) {
             nc = locate(next_tile);
             S.coord[(it + 1u) & 1u] = nc;
         }
+#endif
         __syncthreads();  // [stage free]
         if (tid == 32) issue(nc);
 
@@ -526,55 +612,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     while (q_count) {  // the tiles still pending
         const unsigned long long tb = wait_base((uint32_t)S.q[q_head].coord.w);
         retire(q_head, tb);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_fscan: exclusive scan of the per-piece triangle counts in voxel-major (row, piece) order --
-// single pass, decoupled look-back over tiles of 2048 pieces.  f8[i] = index of the first face of
-// piece 8*i; the grand total goes to the header.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fscan(McGeom g, McWorkspace ws) {
-    __shared__ unsigned long long s_warp[8];
-    __shared__ unsigned long long s_excl;
-    __shared__ unsigned int s_tile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ws.header->ticket_scan, 1u);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= g.nscan) break;
-        const int64_t r0 = tile * kFscanTile + (int64_t)threadIdx.x * 8;
-        uint32_t c[8];
-        if (r0 + 8 <= g.npieces) {
-            const uint4 lo = *reinterpret_cast<const uint4 *>(ws.nf + r0), hi = *reinterpret_cast<const uint4 *>(ws.nf + r0 + 4);
-            c[0] = lo.x, c[1] = lo.y, c[2] = lo.z, c[3] = lo.w, c[4] = hi.x, c[5] = hi.y, c[6] = hi.z, c[7] = hi.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] = (r0 + j < g.npieces) ? ws.nf[r0 + j] : 0u;
-        }
-        unsigned long long sum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += c[j];
-        const unsigned long long incl = warp_incl_scan64(sum, lane);
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned long long before = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const unsigned long long a = s_warp[k];
-            if (k < warp) before += a;
-            total += a;
-        }
-        if (warp == 0) {
-            const unsigned long long e = lookback(ws.status_f, tile, total, lane);
-            if (lane == 0) {
-                s_excl = e;
-                if (tile == g.nscan - 1) ws.header->total_f = e + total;
-            }
-        }
-        __syncthreads();
-        if (r0 < g.npieces) ws.f8[r0 >> 3] = s_excl + before + incl - sum;
     }
 }
 
@@ -595,6 +632,12 @@ __global__ void __launch_bounds__(256) k_fscan(McGeom g, McWorkspace ws) {
 // and one formula serves all twelve:  id = first id of mask q + popc(mask q & bits below z + up).
 // All global loads of a group are issued in one batch; the triangle counts of the NEXT group (the early-out
 // test) are fetched one iteration ahead.
+//
+// Work distribution and face offsets: a warp takes chunks of kFaceChunk consecutive groups (128 pieces) by
+// ticket.  The index of a chunk's first face is the sum of the rounds before its round and of the chunks before
+// it in its round (sums accumulated by k_tile: final data, one batch of loads, nobody waits for anybody); the
+// groups' first indices follow from an exclusive scan of the chunk's own counts (4 pieces per lane).  There is
+// no scan kernel and no per-piece offset array.
 // ---------------------------------------------------------------------------------------------
 constexpr uint64_t kEdgeToEntry = (0ull << 0) | (3ull << 4) | (5ull << 8) | (1ull << 12) | (8ull << 16) | (11ull << 20) |
                                   (13ull << 24) | (9ull << 28) | (2ull << 32) | (4ull << 36) | (7ull << 40) |
@@ -604,11 +647,7 @@ constexpr int kFaceWarps = 4;
 #define P3D_FACE_CTAS 6
 #endif
 constexpr int kFaceCtasPerSm = P3D_FACE_CTAS;
-constexpr int kFacePieces = 16;    // pieces per warp iteration (a "group")
-#ifndef P3D_FACE_CHUNK
-#define P3D_FACE_CHUNK 8
-#endif
-constexpr int kFaceChunk = P3D_FACE_CHUNK;  // groups per ticket
+static_assert(kFacePieces * kFaceChunk == 128, "a chunk is 4 pieces per lane");
 constexpr int kFaceSlots = 64;     // bit words per warp iteration
 constexpr int kCellCap = 256;
 constexpr int kTriBatch = 160;     // triangles of one batch of 32 cells (<= 5 each)
@@ -619,6 +658,7 @@ struct FaceScratch {
     uint2 rank[kFaceSlots * kRankStride];  // per word slot and mask q: {mask, id of its first crossing (+ vertex_id_base)}
     uint16_t cell[kCellCap];              // slot<<5 | bit
     uint32_t tri[kTriBatch];              // slot<<5 | bit | three entry nibbles << 12
+    unsigned long long gbase[16];         // index of the first face of each group of the (up to two) chunks in flight
 };
 constexpr int kFaceSmemBytes = 256 * (int)sizeof(uint64_t) + kFaceWarps * (int)sizeof(FaceScratch);
 
@@ -660,26 +700,55 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
 
     // ---- work distribution: chunks of kFaceChunk consecutive groups by ticket (the cost of a group follows the
     // surface, so a static round-robin leaves SMs idle at the end); the ticket of the next chunk is taken a
-    // chunk ahead of its use ----
+    // chunk ahead of its use.  The first face index of each group of a chunk is parked in shared memory
+    // (two chunks can be in the pipeline at once: slots 0-7 and 8-15 alternate). ----
+    const uint32_t nchunks = (uint32_t)g.nchunks;
     uint32_t ticket_ahead = 0;
     auto take_ticket = [&]() {
         if (lane == 0) ticket_ahead = atomicAdd(&ws.header->ticket_faces, 1u);
     };
     take_ticket();
-    int64_t chunk_cur = 0, chunk_end = 0;
+    uint32_t chunk_id = 0, chunk_j = 0, chunk_n = 0, chunk_slot = 8;
     bool exhausted = false;
-    auto next_group = [&]() -> int64_t {
-        if (chunk_cur == chunk_end && !exhausted) {
-            chunk_cur = (int64_t)__shfl_sync(kFull, ticket_ahead, 0) * kFaceChunk;
-            chunk_end = chunk_cur + kFaceChunk < ngroups ? chunk_cur + kFaceChunk : ngroups;
-            if (chunk_cur >= ngroups) {
+    auto next_group = [&](uint32_t &slot) -> int64_t {
+        if (chunk_j == chunk_n && !exhausted) {
+            chunk_id = __shfl_sync(kFull, ticket_ahead, 0);
+            if (chunk_id >= nchunks) {
                 exhausted = true;
-                chunk_cur = chunk_end = 0;
             } else {
                 take_ticket();
+                const int64_t first_group = (int64_t)chunk_id * kFaceChunk;
+                chunk_j = 0;
+                chunk_n = (uint32_t)(first_group + kFaceChunk < ngroups ? kFaceChunk : ngroups - first_group);
+                chunk_slot ^= 8u;
+                // everything in one batch of loads: my four counts, the rounds before, the chunks before in the round
+                const int64_t p0 = first_group * kFacePieces + 4 * lane;
+                uint4 n4 = make_uint4(0u, 0u, 0u, 0u);
+                if (p0 + 4 <= g.npieces) {
+                    n4 = __ldg(reinterpret_cast<const uint4 *>(ws.nf + p0));
+                } else {
+                    if (p0 < g.npieces) n4.x = __ldg(ws.nf + p0);
+                    if (p0 + 1 < g.npieces) n4.y = __ldg(ws.nf + p0 + 1);
+                    if (p0 + 2 < g.npieces) n4.z = __ldg(ws.nf + p0 + 2);
+                }
+                const uint32_t round = chunk_id / kRoundTiles, in_round = chunk_id % kRoundTiles;
+                unsigned long long acc = 0;
+                const uint32_t *cs = ws.chunk_sum + (chunk_id - in_round);
+#pragma unroll
+                for (int i = 0; i < kRoundTiles / 32; ++i)
+                    if ((uint32_t)(lane + 32 * i) < in_round) acc += __ldg(cs + lane + 32 * i);
+#pragma unroll 4
+                for (uint32_t r = lane; r < round; r += 32) acc += __ldg(ws.fround_sum + r);
+                const unsigned long long chunk_face = warp_sum64(acc);
+                const uint32_t mine = n4.x + n4.y + n4.z + n4.w, excl = warp_incl_scan(mine, lane) - mine;
+                // group j of the chunk = pieces 16 j .. 16 j + 15 = lanes 4 j .. 4 j + 3
+                if ((lane & 3) == 0) sc.gbase[chunk_slot + (lane >> 2)] = chunk_face + excl;
+                __syncwarp();
             }
         }
-        return exhausted ? -1 : chunk_cur++;
+        if (exhausted) return -1;
+        slot = chunk_slot + chunk_j;
+        return (int64_t)chunk_id * kFaceChunk + chunk_j++;
     };
     auto group_counts = [&](int64_t gr) {  // triangle count of my piece of group gr
         const int64_t i = gr * kFacePieces + (lane >> 1);
@@ -690,14 +759,12 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
     uint4 ta, tb, td, tcc;            // table entries of my piece in rows a (x,y), b (x+1,y), d (x,y+1), c (x+1,y+1)
     uint32_t A[3], B[3], C[3], D[3];  // my two bit words of the four rows and the word after them
     uint32_t nax, nay, nby, ndx;      // lane 31: entries of the piece after mine (for the cell at bit 127)
-    unsigned long long fbase_ld;      // lane 0: index of the group's first face
     int p_ld;                         // my piece index within its row
     auto issue_loads = [&](int64_t gr, uint32_t nf) {
         ta = make_uint4(0, 0, 0, 0), tb = ta, td = ta, tcc = ta;
 #pragma unroll
         for (int i = 0; i < 3; ++i) A[i] = B[i] = C[i] = D[i] = 0u;
         nax = nay = nby = ndx = 0u;
-        fbase_ld = 0;
         p_ld = 0;
         if (!__any_sync(kFull, nf != 0u)) return;
         const int64_t gi = gr * kFacePieces + (lane >> 1);
@@ -735,15 +802,15 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
             C[0] = c2.x, C[1] = c2.y, C[2] = more ? __ldg(pc + 2) : 0u;
             D[0] = d2.x, D[1] = d2.y, D[2] = more ? __ldg(pd + 2) : 0u;
         }
-        if (lane == 0) fbase_ld = ws.f8[gr * (kFacePieces / 8)];
     };
 
-    int64_t g0 = next_group(), g1 = next_group();
+    uint32_t fs0 = 0, fs1 = 0, fs2 = 0;  // gbase slots of groups g0, g1, g2
+    int64_t g0 = next_group(fs0), g1 = next_group(fs1);
     uint32_t nf0 = group_counts(g0), nf1 = group_counts(g1);  // != 0 only for rows with x + 1 < rx and y + 1 < ry (k_tile)
     issue_loads(g0, nf0);
 
     while (g0 >= 0) {
-        const int64_t g2 = next_group();
+        const int64_t g2 = next_group(fs2);
         const uint32_t nf2 = group_counts(g2);
         const uint32_t nf = nf0;
         const bool active = __any_sync(kFull, nf != 0u);
@@ -760,7 +827,7 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                 const uint32_t s2 = __shfl_down_sync(kFull, tb.y, 2), s3 = __shfl_down_sync(kFull, td.x, 2);
                 xax = lane < 30 ? s0 : nax, xay = lane < 30 ? s1 : nay, xby = lane < 30 ? s2 : nby, xdx = lane < 30 ? s3 : ndx;
             }
-            fbase = __shfl_sync(kFull, fbase_ld, 0);
+            fbase = sc.gbase[fs0];
             finc = warp_incl_scan(h ? 0u : nf, lane);  // faces of the pieces up to and including mine
 
             // the eight masks of my word w (samples outside the grid were staged as 0.0f in every row, so the x/y
@@ -858,6 +925,17 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                     __syncwarp();
                     // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
                     int32_t *const out0 = faces + frun * 3ull;
+#if P3D_FACE_IDX
+                    // one face index per lane: consecutive lanes write consecutive words
+                    for (uint32_t j = lane; j < 3u * btot; j += 32) {
+                        const uint32_t t = (j * 0xAAABu) >> 17, cc = j - 3u * t;  // j / 3, j % 3
+                        const uint32_t ent = sc.tri[t];
+                        const uint32_t nib = ent >> (12u + 4u * cc);
+                        const uint2 en = sc.rank[((ent >> 5) & 63u) * kRankStride + (nib & 7u)];
+                        const uint32_t below = (((nib & 8u) ? 2u : 1u) << (ent & 31u)) - 1u;  // bits below z / below z+1
+                        out0[j] = (int32_t)(en.y + __popc(en.x & below));
+                    }
+#else
                     for (uint32_t j = lane; j < btot; j += 32) {
                         const uint32_t ent = sc.tri[j];
                         const uint32_t i = ent & 31u;
@@ -871,6 +949,7 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                             out[cc] = (int32_t)(en.y + __popc(en.x & ((nib & 8u) ? below1 : below0)));
                         }
                     }
+#endif
                     __syncwarp();
                     frun += btot;
                 }
@@ -891,8 +970,8 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
             }
             __syncwarp();
         }
-        g0 = g1, nf0 = nf1;
-        g1 = g2, nf1 = nf2;
+        g0 = g1, nf0 = nf1, fs0 = fs1;
+        g1 = g2, nf1 = nf2, fs1 = fs2;
     }
 }
 
@@ -985,14 +1064,24 @@ void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws,
         launch_tile_kernel<false>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
 }
 
-void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
-    if (g.nscan <= 0) return;
-    const int64_t cap = (int64_t)sm_count() * 4;
-    k_fscan<<<(unsigned)(g.nscan < cap ? g.nscan : cap), 256, 0, s>>>(g, ws);
+// triangles of each round of 256 chunks (a CTA per round)
+__global__ void __launch_bounds__(kRoundTiles) k_round_sums(McGeom g, McWorkspace ws) {
+    __shared__ unsigned long long s_warp[kRoundTiles / 32];
+    const int64_t c = (int64_t)blockIdx.x * kRoundTiles + threadIdx.x;
+    const unsigned long long v = warp_sum64(c < g.nchunks ? ws.chunk_sum[c] : 0u);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int i = 0; i < kRoundTiles / 32; ++i) t += s_warp[i];
+        ws.fround_sum[blockIdx.x] = t;
+    }
 }
 
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s) {
     if (g.npieces <= 0) return;
+    k_round_sums<<<(unsigned)g.nfrounds, kRoundTiles, 0, s>>>(g, ws);
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
     const int64_t want = ((groups + kFaceChunk - 1) / kFaceChunk + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * kFaceCtasPerSm;
     static const bool attr = [] {

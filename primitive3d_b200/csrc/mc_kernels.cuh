@@ -13,11 +13,14 @@
 //                     reference's operation order (marching_cubes.cu:105-109, :298).
 //                     Side products: bit words, one 16-byte table entry per (row, 128-sample
 //                     piece) = first id of its x-/y-/z-edge vertices + its triangle count.
-//           k_fscan   exclusive scan (look-back, no CUB/thrust) of the per-piece triangle
-//                     counts in voxel-major order.
-//   pass B  k_faces   a lane per piece: recomputes crossing masks from the bit words, ranks
-//                     any cube edge as table base + popc(mask below z), and writes faces in
-//                     voxel-major cell order, table order inside a cell (marching_cubes.cu:194-208).
+//                     Triangle counts are also summed (RED) per chunk of 128 consecutive (row, piece)
+//                     pairs and per round of 256 chunks, in voxel-major order.
+//   pass B  k_faces   warps take chunks by ticket; a chunk's first face index is the sum of the
+//                     rounds before its round and of the chunks before it in its round (one batch
+//                     of loads of final data: no scan kernel, no CUB/thrust, no waiting).  A lane
+//                     per half piece recomputes crossing masks from the bit words, ranks any cube
+//                     edge as table base + popc(mask below z), and writes faces in voxel-major cell
+//                     order, table order inside a cell (marching_cubes.cu:194-208).
 //
 // Vertex numbering (a free choice: the reference's is atomicAdd-arbitrary): tiles in a fixed
 // order that depends on the grid shape only; inside a tile, (x,y) rows in C order; inside a
@@ -36,7 +39,9 @@ constexpr int kBoxZ = kTileZ + 4;                    // staged samples per row: 
 constexpr int kBoxRows = (kTileX + 1) * (kTileY + 1);
 constexpr int kStageBytes = ((kBoxRows * kBoxZ * 4 + 127) / 128) * 128;
 constexpr int kTileThreads = 256;                    // one thread per owned bit word
-constexpr int kFscanTile = 2048;                     // pieces per scan tile (256 threads x 8)
+constexpr int kFacePieces = 16;                      // pieces per warp iteration of the face pass (a "group")
+constexpr int kFaceChunk = 8;                        // groups per ticket: 128 pieces, 4 per lane
+constexpr int kRoundTiles = 256;                     // scan items (tiles / face chunks) per round of the two-level scan
 
 struct McGeom {
     int64_t rx, ry, rz;   // local dims (rx includes the halo plane, if any)
@@ -46,31 +51,36 @@ struct McGeom {
     int32_t band;         // y-blocks per band of the tile order
     int64_t ntiles;       // nxb * nyb * np
     int64_t npieces;      // owned_x * ry * np
-    int64_t nscan;        // ceil(npieces / kFscanTile)
+    int64_t nchunks;      // ceil(npieces / 128): face-pass chunks
     int64_t nrounds;      // ceil(ntiles / 256): rounds of the tile scan
+    int64_t nfrounds;     // ceil(nchunks / 256): rounds of face chunks
     uint64_t magic_np;    // floor(2^64 / np) + 1: n / np == umul64hi(n, magic_np) for n < 2^32 (np > 1)
 };
 
 // Workspace header (device).  Zeroed before every count.
 struct McHeader {
-    unsigned long long total_v;
-    unsigned long long total_f;
-    unsigned int ticket;       // dynamic tile id of k_tile
-    unsigned int ticket_scan;  // dynamic tile id of k_fscan
-    unsigned int ticket_faces; // dynamic chunk id of k_faces (reset by launch_faces)
-    unsigned int pad[1];
+    unsigned long long total_v;  // written by the last tile
+    unsigned long long total_f;  // accumulated tile by tile (k_tile)
+    unsigned int ticket;         // dynamic tile id of k_tile
+    unsigned int ticket_faces;   // dynamic chunk id of k_faces (reset by launch_faces)
+    unsigned int pad[2];
+};
+
+// State of one single-pass scan (two levels: items, rounds of 256 items).  Zeroed before use.
+struct McScan {
+    unsigned long long *status;        // [n] published count of each item
+    unsigned long long *round_acc;     // [rounds] arrivals<<48 | sum of each round
+    unsigned long long *round_prefix;  // [rounds + 1] published exclusive prefix of each round
 };
 
 struct McWorkspace {
     McHeader *header;
-    unsigned long long *status;    // [ntiles] published vertex count of each tile (k_tile)
-    unsigned long long *round_acc;     // [nrounds] arrivals<<48 | vertex count of each round of 256 tiles
-    unsigned long long *round_prefix;  // [nrounds + 1] published exclusive vertex prefix of each round
-    unsigned long long *status_f;  // [nscan]  look-back status words of k_fscan
+    McScan vscan;                  // vertex counts over tiles (k_tile)
+    uint32_t *chunk_sum;           // [nchunks] triangles of each chunk of 128 consecutive pieces (k_tile, RED)
+    unsigned long long *fround_sum;  // [nfrounds] triangles of each round of 256 chunks (k_tile, RED)
     uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: ids of the piece's first x-/y-/z-edge vertex (relative to
                                    // the tile until the tile's first id is known, absolute after the tile pass)
-    uint32_t *nf;                  // [npieces] triangles per piece (input of k_fscan)
-    unsigned long long *f8;        // [ceil(npieces/8)] index of the first face of pieces 8i..
+    uint32_t *nf;                  // [npieces] triangles per piece
     uint32_t *bits;                // [rx*ry][4*np] inside bits, 32 samples per word
 };
 
@@ -86,7 +96,6 @@ struct McEmitParams {
 // mode 1: vertices only, after a completed mode-0 pass on the same workspace.
 void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
                       int64_t vertex_capacity, int mode, cudaStream_t s);
-void launch_face_scan(const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s);
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);

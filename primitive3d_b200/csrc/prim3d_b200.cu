@@ -49,15 +49,16 @@ bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
     g->band = (int32_t)band;
     g->ntiles = (int64_t)g->nxb * g->nyb * g->np;
     g->npieces = d->owned_x * d->ry * g->np;
-    g->nscan = (g->npieces + p3d::kFscanTile - 1) / p3d::kFscanTile;
-    g->nrounds = (g->ntiles + 255) / 256;
+    g->nchunks = (g->npieces + p3d::kFacePieces * p3d::kFaceChunk - 1) / (p3d::kFacePieces * p3d::kFaceChunk);
+    g->nrounds = (g->ntiles + p3d::kRoundTiles - 1) / p3d::kRoundTiles;
+    g->nfrounds = (g->nchunks + p3d::kRoundTiles - 1) / p3d::kRoundTiles;
     g->magic_np = g->np > 1 ? ~0ull / (uint64_t)g->np + 1 : 0;
     if (g->ntiles > ((int64_t)1 << 31) || d->rx * d->ry * (int64_t)g->np > ((int64_t)1 << 40)) return false;
     return true;
 }
 
 struct Layout {
-    size_t header, status, round_acc, round_prefix, status_f, zero_end, ptab, nf, f8, bits, total;
+    size_t header, status, round_acc, round_prefix, chunk_sum, fround_sum, zero_end, ptab, nf, bits, total;
 };
 
 Layout make_layout(const p3d::McGeom &g) {
@@ -68,11 +69,11 @@ Layout make_layout(const p3d::McGeom &g) {
     l.status = off;   off += align_up((size_t)g.ntiles * 8);
     l.round_acc = off;    off += align_up((size_t)g.nrounds * 8);
     l.round_prefix = off; off += align_up((size_t)(g.nrounds + 1) * 8);
-    l.status_f = off; off += align_up((size_t)g.nscan * 8);
+    l.chunk_sum = off;    off += align_up((size_t)g.nchunks * 4);
+    l.fround_sum = off;   off += align_up((size_t)g.nfrounds * 8);
     l.zero_end = off;  // everything above is zeroed before a count
     l.ptab = off;     off += align_up(all_pieces * sizeof(uint4));
     l.nf = off;       off += align_up((size_t)g.npieces * 4 + 32);
-    l.f8 = off;       off += align_up(((size_t)g.npieces / 8 + 1) * 8);
     l.bits = off;     off += align_up(all_pieces * 16);
     l.total = off;
     return l;
@@ -82,13 +83,13 @@ p3d::McWorkspace bind(void *base, const Layout &l) {
     char *b = static_cast<char *>(base);
     p3d::McWorkspace ws;
     ws.header = reinterpret_cast<p3d::McHeader *>(b + l.header);
-    ws.status = reinterpret_cast<unsigned long long *>(b + l.status);
-    ws.round_acc = reinterpret_cast<unsigned long long *>(b + l.round_acc);
-    ws.round_prefix = reinterpret_cast<unsigned long long *>(b + l.round_prefix);
-    ws.status_f = reinterpret_cast<unsigned long long *>(b + l.status_f);
+    ws.vscan.status = reinterpret_cast<unsigned long long *>(b + l.status);
+    ws.vscan.round_acc = reinterpret_cast<unsigned long long *>(b + l.round_acc);
+    ws.vscan.round_prefix = reinterpret_cast<unsigned long long *>(b + l.round_prefix);
+    ws.chunk_sum = reinterpret_cast<uint32_t *>(b + l.chunk_sum);
+    ws.fround_sum = reinterpret_cast<unsigned long long *>(b + l.fround_sum);
     ws.ptab = reinterpret_cast<uint4 *>(b + l.ptab);
     ws.nf = reinterpret_cast<uint32_t *>(b + l.nf);
-    ws.f8 = reinterpret_cast<unsigned long long *>(b + l.f8);
     ws.bits = reinterpret_cast<uint32_t *>(b + l.bits);
     return ws;
 }
@@ -158,11 +159,10 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const p3d::McWorkspace ws = bind(workspace, l);
 
-    // header + both look-back status arrays are contiguous: one memset
+    // header, the tile scan state and the chunk sums are contiguous: one memset
     P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
     p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
     if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_count: ") + p3d::tile_pass_error());
-    p3d::launch_face_scan(g, ws, s);
     P3D_CUDA(cudaGetLastError());
 
     int64_t *pin = pinned_counts();
@@ -219,8 +219,7 @@ p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *
             p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
             if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, p3d::tile_pass_error());
             break;
-        case 2: p3d::launch_face_scan(g, ws, s); break;
-        default: return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: stage must be 0, 1 or 2");
+        default: return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: stage must be 0 or 1");
     }
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
