@@ -19,6 +19,12 @@
 #ifndef P3D_FACE_IDX
 #define P3D_FACE_IDX 0
 #endif
+#ifndef P3D_BITS_WORD
+#define P3D_BITS_WORD 1
+#endif
+#ifndef P3D_COUNT_EULER
+#define P3D_COUNT_EULER 1
+#endif
 
 namespace p3d {
 
@@ -30,6 +36,22 @@ __constant__ uint64_t c_case_table[256] = P3D_MC_CASE_TABLE_INIT;
 // Bits of word w (32 samples from z = 32*w) with z + 1 < rz: samples that own a +z edge / a cell.
 __device__ __forceinline__ uint32_t low_mask(int64_t n) {
     return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (int)n) - 1u));
+}
+
+// inside bits (value > thresh, marching_cubes.cu:25) of 32 consecutive staged samples, by ONE thread: eight
+// 16-byte shared-memory reads, then a compare and a predicated OR per sample (NaN compares false, like the
+// reference's `>`).  Four accumulators keep the OR chains short.
+__device__ __forceinline__ uint32_t inside_word(const float *src, float thresh) {
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 f = *reinterpret_cast<const float4 *>(src + 4 * j);
+        asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(w0) : "f"(f.x), "f"(thresh), "r"(1u << (4 * j)));
+        asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(w1) : "f"(f.y), "f"(thresh), "r"(2u << (4 * j)));
+        asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(w2) : "f"(f.z), "f"(thresh), "r"(4u << (4 * j)));
+        asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}" : "+r"(w3) : "f"(f.w), "f"(thresh), "r"(8u << (4 * j)));
+    }
+    return (w0 | w1) | (w2 | w3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,7 +194,8 @@ struct TileSmem {
     uint16_t nfp[kTileX * kTileY];  // triangles of each owned (row, piece)
     float dt[kRing];       // pending vertices: interpolation parameter ...
     uint16_t ent[kRing];   // ... and edge (axis<<13 | row<<7 | z)
-    uint8_t ntri[256];     // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1
+    int8_t ntri[256];      // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1: #triangles of the
+                           // case, or (P3D_COUNT_EULER) its correction  #triangles - (#crossed edges - 2)
     PendingTile q[kQueue];
     unsigned long long bar;
     unsigned long long base;       // result of warp 0's non-blocking look-back at the top of an iteration
@@ -205,7 +228,17 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t c = tid;
         const uint32_t cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
                             ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
-        S.ntri[c] = (uint8_t)(c_case_table[cs] >> 60);
+        const int nt = (int)(c_case_table[cs] >> 60);
+#if P3D_COUNT_EULER
+        // crossed edges of the case, cube edges in the numbering of marching_cubes.cu:178-192
+        const int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+        int ne = 0;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) ne += (int)(((cs >> ea[e]) ^ (cs >> eb[e])) & 1u);
+        S.ntri[c] = (int8_t)(ne ? nt - (ne - 2) : 0);
+#else
+        S.ntri[c] = (int8_t)nt;
+#endif
     }
 
     // Tile id -> coordinates.  Tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
@@ -386,6 +419,21 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // ---- phase 1: inside bits of the 81 staged rows.  inside = value > thresh (:25,31,37,43,50-57).
         // Samples outside the grid are staged as 0.0f; their bits take part in no mask that is not cut by a
         // validity test below, so they need no cleaning here. ----
+#if P3D_BITS_WORD
+        {
+            // a thread per (staged row, word): the eight lanes of a quarter warp read eight consecutive rows at the
+            // same word, i.e. eight different 16-byte bank groups (a staged row is 33 x 16 bytes)
+            const int brow = warp * 8 + (lane & 7), bword = lane >> 3;
+            S.sbits[brow * kSbitsStride + bword] = inside_word(tf + brow * kBoxZ + 32 * bword, thresh);
+            if (warp < 3) {  // staged rows 64 .. 80
+                const int row2 = 64 + brow;
+                if (row2 < kBoxRows) S.sbits[row2 * kSbitsStride + bword] = inside_word(tf + row2 * kBoxZ + 32 * bword, thresh);
+            } else if (warp < 6) {  // the halo sample (z0 + 128) of every staged row: a lane per row
+                const int row = (warp - 3) * 32 + lane;
+                if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
+            }
+        }
+#else
         {
             auto row_bits = [&](int row) {
                 const float *src = tf + row * kBoxZ + lane;
@@ -404,6 +452,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
             }
         }
+#endif
         __syncthreads();  // [bits]
 #if P3D_TILE_PREFETCH
         // the next tile's box is pulled into L2 now, so that the TMA load issued when the stage is free lands fast
@@ -429,6 +478,38 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t m1 = hy ? (A ^ D) : 0u;            // +y edges, :35-39 / :113-124
         const uint32_t m2 = own ? ((A ^ A2) & zv) : 0u;   // +z edges, :41-45 / :126-137
         uint32_t nf = 0;
+#if P3D_COUNT_EULER
+        // Triangles of my 32 cells without walking them.  Every row of the case table triangulates the closed
+        // loops the surface cuts through the cell, a loop over k crossed edges into k - 2 triangles, so a cell
+        // with E crossed edges and L loops has E - 2 L triangles (checked for all 256 cases, tests/test_tables.py).
+        // E summed over the word is twelve popcounts; L = 1 unless the inside or the outside corners fall apart,
+        // which needs an ambiguous face (all four edges of a face crossed) or two isolated opposite corners:
+        // only those cells are looked up, for their correction  #triangles - (E - 2).
+        if (hc) {                                         // cells :48-66; bit i = cell at sample z0 + 32 w + i
+            const uint32_t B2 = __funnelshift_r(B, Bn, 1), C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
+            const uint32_t xa0 = (A ^ B) & zv, xa1 = (A2 ^ B2) & zv, xd0 = (D ^ C) & zv, xd1 = (D2 ^ C2) & zv;  // x edges
+            const uint32_t ya0 = (A ^ D) & zv, ya1 = (A2 ^ D2) & zv, yb0 = (B ^ C) & zv, yb1 = (B2 ^ C2) & zv;  // y edges
+            const uint32_t za = (A ^ A2) & zv, zb = (B ^ B2) & zv, zc = (C ^ C2) & zv, zd = (D ^ D2) & zv;      // z edges
+            const uint32_t act = xa0 | xa1 | xd0 | xd1 | ya0 | ya1 | yb0 | yb1 | za | zb | zc | zd;  // mixed corners
+            const int edges = __popc(xa0) + __popc(xa1) + __popc(xd0) + __popc(xd1) + __popc(ya0) + __popc(ya1) +
+                              __popc(yb0) + __popc(yb1) + __popc(za) + __popc(zb) + __popc(zc) + __popc(zd);
+            // three crossed edges of a face imply the fourth (parity around the face)
+            const uint32_t amb = (xa0 & yb0 & xd0) | (xa1 & yb1 & xd1) | (xa0 & zb & xa1) | (yb0 & zc & yb1) |
+                                 (xd0 & zd & xd1) | (ya0 & za & ya1);
+            const uint32_t pac = za & zc, pbd = zb & zd;
+            const uint32_t diag = (pac & ((xa0 & ya0 & yb1 & xd1) | (yb0 & xd0 & xa1 & ya1))) |   // a0 + c1, c0 + a1 isolated
+                                  (pbd & ((xa0 & yb0 & xd1 & ya1) | (xd0 & ya0 & xa1 & yb1)));    // b0 + d1, d0 + b1 isolated
+            int total = edges - 2 * __popc(act);
+            for (uint32_t rem = amb | diag; rem;) {
+                const int i = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t code = (__funnelshift_r(A, An, i) & 3u) | ((__funnelshift_r(B, Bn, i) & 3u) << 2) |
+                                      ((__funnelshift_r(C, Cn, i) & 3u) << 4) | ((__funnelshift_r(D, Dn, i) & 3u) << 6);
+                total += S.ntri[code];
+            }
+            nf = (uint32_t)total;
+        }
+#else
         if (hc) {                                         // cells with mixed corners, :48-66
             const uint32_t B2 = __funnelshift_r(B, Bn, 1), C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
             const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
@@ -440,6 +521,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 nf += S.ntri[code];
             }
         }
+#endif
         // my (row, piece) = 4 adjacent lanes: packed {nx, ny, nz} (8-bit fields, <= 128 each)
         const uint32_t cnt = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 8) | ((uint32_t)__popc(m2) << 16);
         uint32_t inc = cnt;

@@ -51,6 +51,34 @@ def test_table_structure():
             assert ((c >> a) & 1) != ((c >> b) & 1)
 
 
+def test_triangle_count_is_edges_minus_two_per_loop():
+    """What k_tile's counting relies on (primitive3d_b200/csrc/mc_kernels.cu, P3D_COUNT_EULER): every case has
+    E - 2 L triangles (E crossed edges, L >= 1 loops), and L > 1 only where a face has all four edges crossed or
+    two opposite corners are both isolated -- the cells the kernel looks up one by one."""
+    t = mc.triangle_table()
+    ends = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    faces = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)]
+    opposite = [(0, 6), (1, 7), (2, 4), (3, 5)]
+    neighbours = {v: [b if a == v else a for a, b in ends if v in (a, b)] for v in range(8)}
+    bit = lambda c, k: (c >> k) & 1
+    flagged = 0
+    for c in range(256):
+        ntri = int((t[c] >= 0).sum()) // 3
+        edges = sum(bit(c, a) != bit(c, b) for a, b in ends)
+        if edges == 0:
+            assert ntri == 0
+            continue
+        assert (edges - ntri) % 2 == 0 and (edges - ntri) // 2 >= 1
+        ambiguous = any(bit(c, f[0]) != bit(c, f[1]) and bit(c, f[1]) != bit(c, f[2]) and bit(c, f[2]) != bit(c, f[3])
+                        for f in faces)
+        isolated = lambda v: all(bit(c, n) != bit(c, v) for n in neighbours[v])
+        diagonal = any(isolated(a) and isolated(b) for a, b in opposite)
+        if ntri != edges - 2:
+            assert ambiguous or diagonal, f"case {c} has {(edges - ntri) // 2} loops but would not be looked up"
+        flagged += ambiguous or diagonal
+    assert flagged < 256
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/src/prim3d/Utility/marching_cubes.h"),
                     reason="reference tree not mounted")
 def test_table_matches_reference_header():
