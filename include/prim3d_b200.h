@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 2
+#define P3D_ABI_VERSION 3
 
 typedef enum p3d_status {
     P3D_OK = 0,
@@ -104,6 +104,30 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
  * follow p3d_mc_count on the same workspace and grid.  Asynchronous. */
 p3d_status p3d_mc_vertices(const p3d_mc_desc *desc, const float *grid, void *workspace,
                            float *vertices, int64_t vertex_capacity, void *stream);
+
+/* Fused dtype ingest.  The reference's Python wrapper casts any input to float32 in a separate
+ * pass before the kernels see it (prim3d/utility/marching_cubes.py:86-87; examples/sphere.py
+ * feeds int64).  The *_typed entry points read the grid in its own element type and convert
+ * each sample to float32 (round to nearest even, exactly what the cast does) as the tile is
+ * staged on chip: classification, interpolation and every output are bit-identical to
+ * cast-then-run, without the extra read + write + read of the cast.  float32 grids take the TMA
+ * path; the others are staged with coalesced row loads. */
+typedef enum p3d_dtype {
+    P3D_F32 = 0,
+    P3D_F16 = 1,
+    P3D_BF16 = 2,
+    P3D_F64 = 3,
+    P3D_I64 = 4,
+    P3D_I32 = 5,
+    P3D_I16 = 6,
+    P3D_U8 = 7
+} p3d_dtype;
+
+p3d_status p3d_mc_count_typed(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                              size_t workspace_bytes, float *vertices, int64_t vertex_capacity,
+                              int64_t *counts_host, void *stream);
+p3d_status p3d_mc_vertices_typed(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                                 float *vertices, int64_t vertex_capacity, void *stream);
 
 /* faces: int32[3*F] (device).  Face indices are written as vertex_id_base + local id
  * (vertex_id_base = exclusive prefix of V over lower shards; 0 on a single GPU).  Must follow

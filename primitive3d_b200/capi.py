@@ -60,6 +60,10 @@ def lib():
         L.p3d_mc_count.argtypes = [dp, vp, vp, sz, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_vertices.restype = ctypes.c_int
         L.p3d_mc_vertices.argtypes = [dp, vp, vp, vp, i64, vp]
+        L.p3d_mc_count_typed.restype = ctypes.c_int
+        L.p3d_mc_count_typed.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, i64, ctypes.POINTER(i64), vp]
+        L.p3d_mc_vertices_typed.restype = ctypes.c_int
+        L.p3d_mc_vertices_typed.argtypes = [dp, vp, ctypes.c_int, vp, vp, i64, vp]
         L.p3d_mc_faces.restype = ctypes.c_int
         L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
@@ -102,9 +106,15 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# torch dtype -> p3d_dtype (include/prim3d_b200.h): element types the tile pass reads directly
+GRID_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3, torch.int64: 4, torch.int32: 5,
+               torch.int16: 6, torch.uint8: 7}
+
+
 def _grid_ok(grid):
-    if not (grid.is_cuda and grid.is_contiguous() and grid.dtype == torch.float32 and grid.dim() == 3):
-        raise ValueError("grid must be a contiguous float32 CUDA tensor [Rx,Ry,Rz]")
+    if not (grid.is_cuda and grid.is_contiguous() and grid.dtype in GRID_DTYPES and grid.dim() == 3):
+        raise ValueError("grid must be a contiguous CUDA tensor [Rx,Ry,Rz] of a supported dtype")
+    return GRID_DTYPES[grid.dtype]
 
 
 def mc_workspace_bytes(desc):
@@ -120,7 +130,7 @@ def mc_count(desc, grid, workspace=None, vertex_capacity=None):
     vbuf is a float32 [vertex_capacity, 3] tensor holding every vertex with id < vertex_capacity
     (all of them when V <= vertex_capacity).  vertex_capacity=None asks the library for its hint,
     0 writes no vertices.  Synchronises the current stream."""
-    _grid_ok(grid)
+    dtype = _grid_ok(grid)
     nbytes = mc_workspace_bytes(desc)
     if workspace is None:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
@@ -129,8 +139,9 @@ def mc_count(desc, grid, workspace=None, vertex_capacity=None):
     vbuf = torch.empty((int(vertex_capacity), 3), dtype=torch.float32, device=grid.device)
     counts = (ctypes.c_int64 * 2)()
     with torch.cuda.device(grid.device):
-        check(lib().p3d_mc_count(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), workspace.numel(),
-                                 vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity), counts, _stream()))
+        check(lib().p3d_mc_count_typed(ctypes.byref(desc), grid.data_ptr(), dtype, workspace.data_ptr(), workspace.numel(),
+                                       vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity), counts,
+                                       _stream()))
     return counts[0], counts[1], workspace, vbuf
 
 
@@ -141,8 +152,8 @@ def mc_vertices(desc, grid, workspace, V, vbuf=None):
         return vbuf[:V]
     verts = torch.empty((V, 3), dtype=torch.float32, device=grid.device)
     with torch.cuda.device(grid.device):
-        check(lib().p3d_mc_vertices(ctypes.byref(desc), grid.data_ptr(), workspace.data_ptr(), verts.data_ptr(), int(V),
-                                    _stream()))
+        check(lib().p3d_mc_vertices_typed(ctypes.byref(desc), grid.data_ptr(), _grid_ok(grid), workspace.data_ptr(),
+                                          verts.data_ptr(), int(V), _stream()))
     return verts
 
 

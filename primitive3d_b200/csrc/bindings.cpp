@@ -36,15 +36,33 @@ void check_status(p3d_status st, const char *what) {
     TORCH_CHECK(st == P3D_OK, what, " failed (status ", static_cast<int>(st), "): ", p3d_last_error());
 }
 
+// element type of a grid the kernels can read directly (p3d_dtype), or -1
+int grid_dtype(const Tensor &t) {
+    switch (t.scalar_type()) {
+        case torch::kFloat: return P3D_F32;
+        case torch::kHalf: return P3D_F16;
+        case torch::kBFloat16: return P3D_BF16;
+        case torch::kDouble: return P3D_F64;
+        case torch::kLong: return P3D_I64;
+        case torch::kInt: return P3D_I32;
+        case torch::kShort: return P3D_I16;
+        case torch::kByte: return P3D_U8;
+        default: return -1;
+    }
+}
+
 // prim3d::marching_cubes, marching_cubes.cu:212-305: same signature, same outputs
-// ([vertices float32 [V,3], faces int32 [F,3]] on the input's device).
+// ([vertices float32 [V,3], faces int32 [F,3]] on the input's device).  The reference accepts float32 only
+// (data_ptr<float>() throws otherwise) and leaves the cast to its Python wrapper; here float16 / bfloat16 /
+// float64 / int64 / int32 / int16 / uint8 grids are also read directly, each sample converted to float32 on
+// chip exactly like `.to(torch.float32)` would (fused dtype ingest).
 std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thresh, const std::vector<float> lower,
                                    const std::vector<float> upper) {
     P3D_CHECK_CUDA(density_grid);
     P3D_CHECK_CONTIGUOUS(density_grid);
     TORCH_CHECK(density_grid.ndimension() == 3);
-    TORCH_CHECK(density_grid.scalar_type() == torch::kFloat, "expected scalar type Float but found ",
-                density_grid.scalar_type());
+    const int dtype = grid_dtype(density_grid);
+    TORCH_CHECK(dtype >= 0, "expected scalar type Float but found ", density_grid.scalar_type());
     TORCH_CHECK(lower.size() == 3 && upper.size() == 3, "lower and upper must have 3 elements");
 
     const c10::cuda::CUDAGuard guard(density_grid.device());
@@ -78,11 +96,12 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
         auto it = g_last_vertex_count.find(key);
         if (it != g_last_vertex_count.end()) cap = std::min<int64_t>(it->second + it->second / 16 + 4096, INT32_MAX);
     }
-    Tensor vbuf = torch::empty({cap, 3}, density_grid.options());
+    const auto f32_opt = density_grid.options().dtype(torch::kFloat);
+    Tensor vbuf = torch::empty({cap, 3}, f32_opt);
 
     int64_t counts[2] = {0, 0};
-    check_status(p3d_mc_count(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), ws_bytes,
-                              vbuf.data_ptr<float>(), cap, counts, stream),
+    check_status(p3d_mc_count_typed(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(), ws_bytes,
+                                    vbuf.data_ptr<float>(), cap, counts, stream),
                  "p3d_mc_count");
     {
         std::lock_guard<std::mutex> lock(g_capacity_mutex);
@@ -97,9 +116,9 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
         const int64_t wasted = (cap - counts[0]) * 12;
         if (wasted > std::max<int64_t>(int64_t(64) << 20, counts[0] * 12)) vertices = vertices.clone();
     } else {
-        vertices = torch::empty({counts[0], 3}, density_grid.options());
-        check_status(p3d_mc_vertices(&desc, density_grid.data_ptr<float>(), workspace.data_ptr(), vertices.data_ptr<float>(),
-                                     counts[0], stream),
+        vertices = torch::empty({counts[0], 3}, f32_opt);
+        check_status(p3d_mc_vertices_typed(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(),
+                                           vertices.data_ptr<float>(), counts[0], stream),
                      "p3d_mc_vertices");
     }
     Tensor faces = torch::empty({counts[1], 3}, density_grid.options().dtype(torch::kInt));

@@ -3,6 +3,8 @@
 #include "mc_kernels.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +39,17 @@ __constant__ uint64_t c_case_table[256] = P3D_MC_CASE_TABLE_INIT;
 __device__ __forceinline__ uint32_t low_mask(int64_t n) {
     return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (int)n) - 1u));
 }
+
+// One grid sample as float32: the conversion `density_grid.to(torch.float32)` performs
+// (prim3d/utility/marching_cubes.py:86-87), round to nearest even.
+__device__ __forceinline__ float sample_f32(float v) { return v; }
+__device__ __forceinline__ float sample_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float sample_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float sample_f32(double v) { return __double2float_rn(v); }
+__device__ __forceinline__ float sample_f32(long long v) { return __ll2float_rn(v); }
+__device__ __forceinline__ float sample_f32(int v) { return __int2float_rn(v); }
+__device__ __forceinline__ float sample_f32(short v) { return (float)v; }
+__device__ __forceinline__ float sample_f32(unsigned char v) { return (float)v; }
 
 // inside bits (value > thresh, marching_cubes.cu:25) of 32 consecutive staged samples, by ONE thread: eight
 // 16-byte shared-memory reads, then a compare and a predicated OR per sample (NaN compares false, like the
@@ -206,9 +219,9 @@ struct TileSmem {
 constexpr int kTileSmemBytes = kStageBytes + (int)sizeof(TileSmem) + 128;
 static_assert(4 * (kTileSmemBytes + 1024) <= 228 * 1024, "k_tile is tuned for four CTAs per SM");
 
-template <bool TMA>
+template <bool TMA, typename T>
 __global__ void __launch_bounds__(kTileThreads, 4)
-    k_tile(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ grid, McGeom g, McWorkspace ws,
+    k_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ grid, McGeom g, McWorkspace ws,
            McEmitParams prm, float *__restrict__ verts, unsigned long long vcap, int mode) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -407,11 +420,16 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         if (TMA) {
             mbar_wait(smem_u32(&S.bar), it & 1u);
         } else {
-            for (int idx = tid; idx < kBoxRows * kBoxZ; idx += kTileThreads) {
-                const int rr = idx / kBoxZ, c = idx - rr * kBoxZ;
+            // a warp per staged row, consecutive lanes on consecutive samples; converted to float32 here
+            for (int rr = warp; rr < kBoxRows; rr += kTileThreads / 32) {
                 const int bx = rr / kRowPitch, by = rr - bx * kRowPitch;
-                const int gx = x0 + bx, gy = y0 + by, gz = z0 + c;
-                tf[idx] = (gx < rx && gy < ry && gz < rz) ? __ldg(grid + ((int64_t)gx * ry + gy) * rz + gz) : 0.0f;
+                const int gx = x0 + bx, gy = y0 + by;
+                const bool row_ok = gx < rx && gy < ry;
+                const T *src = grid + ((int64_t)(row_ok ? gx : 0) * ry + (row_ok ? gy : 0)) * rz;
+                for (int c = lane; c < kBoxZ; c += 32) {
+                    const int gz = z0 + c;
+                    tf[rr * kBoxZ + c] = (row_ok && gz < rz) ? sample_f32(__ldg(src + gz)) : 0.0f;
+                }
             }
             __syncthreads();
         }
@@ -1089,39 +1107,39 @@ bool force_generic() {
     return v;
 }
 
-template <bool TMA>
-void launch_tile_kernel(const CUtensorMap &map, const float *grid, const McGeom &g, const McWorkspace &ws,
+template <bool TMA, typename T>
+void launch_tile_kernel(const CUtensorMap &map, const void *grid, const McGeom &g, const McWorkspace &ws,
                         const McEmitParams &p, float *verts, int64_t vcap, int mode, cudaStream_t s) {
     static const bool attr = [] {
-        cudaFuncSetAttribute(k_tile<TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
+        cudaFuncSetAttribute(k_tile<TMA, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
         return true;
     }();
     (void)attr;
-    // every CTA must be resident: tiles are assigned round-robin and wait for lower tile ids
+    // every CTA must be resident: a CTA waits for tiles with lower ids, which running CTAs hold
     static const int per_sm = [] {
         int n = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA>, kTileThreads, kTileSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA, T>, kTileThreads, kTileSmemBytes);
         return n > 0 ? n : 1;
     }();
     const int64_t cap = (int64_t)sm_count() * per_sm;
     const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
-    k_tile<TMA><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, grid, g, ws, p, verts,
-                                                             (unsigned long long)(vcap > 0 ? vcap : 0), mode);
+    k_tile<TMA, T><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, static_cast<const T *>(grid), g, ws, p, verts,
+                                                                (unsigned long long)(vcap > 0 ? vcap : 0), mode);
 }
 
 }  // namespace
 
 const char *tile_pass_error() { return g_tile_error; }
 
-void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
-                      int64_t vertex_capacity, int mode, cudaStream_t s) {
+void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
+                      float *verts, int64_t vertex_capacity, int mode, cudaStream_t s) {
     g_tile_error = nullptr;
     if (g.ntiles <= 0) return;
     if (!verts) vertex_capacity = 0;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     // TMA needs a 16-byte aligned base and 16-byte multiples as row / plane strides
-    bool tma = !force_generic() && (g.rz % 4 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    bool tma = dtype == 0 && !force_generic() && (g.rz % 4 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
     if (tma) {
         EncodeTiledFn enc = encode_tiled();
         if (!enc) {
@@ -1131,7 +1149,7 @@ void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws,
             const cuuint64_t strides[2] = {(cuuint64_t)g.rz * 4, (cuuint64_t)g.ry * (cuuint64_t)g.rz * 4};
             const cuuint32_t box[3] = {kBoxZ, kTileY + 1, kTileX + 1};
             const cuuint32_t estr[3] = {1, 1, 1};
-            const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(grid), dims, strides, box,
+            const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(grid), dims, strides, box,
                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
@@ -1140,10 +1158,21 @@ void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws,
             }
         }
     }
-    if (tma)
-        launch_tile_kernel<true>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
-    else
-        launch_tile_kernel<false>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
+    if (tma) {
+        launch_tile_kernel<true, float>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
+        return;
+    }
+    switch (dtype) {  // p3d_dtype, include/prim3d_b200.h
+        case 0: launch_tile_kernel<false, float>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 1: launch_tile_kernel<false, __half>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 2: launch_tile_kernel<false, __nv_bfloat16>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 3: launch_tile_kernel<false, double>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 4: launch_tile_kernel<false, long long>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 5: launch_tile_kernel<false, int>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 6: launch_tile_kernel<false, short>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        case 7: launch_tile_kernel<false, unsigned char>(map, grid, g, ws, p, verts, vertex_capacity, mode, s); break;
+        default: g_tile_error = "unknown grid dtype"; break;
+    }
 }
 
 // triangles of each round of 256 chunks (a CTA per round)

@@ -94,8 +94,9 @@ struct McEmitParams {
 
 // mode 0: full pass (side products + vertices with id < vertex_capacity);
 // mode 1: vertices only, after a completed mode-0 pass on the same workspace.
-void launch_tile_pass(const float *grid, const McGeom &g, const McWorkspace &ws, const McEmitParams &p, float *verts,
-                      int64_t vertex_capacity, int mode, cudaStream_t s);
+// dtype: p3d_dtype of the grid's elements (include/prim3d_b200.h); every sample is converted to float32 on chip.
+void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
+                      float *verts, int64_t vertex_capacity, int mode, cudaStream_t s);
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s);
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);

@@ -147,7 +147,13 @@ int64_t p3d_mc_plane_table_words(const p3d_mc_desc *desc) {
 
 p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *workspace, size_t workspace_bytes,
                         float *vertices, int64_t vertex_capacity, int64_t *counts_host, void *stream) {
+    return p3d_mc_count_typed(desc, grid, P3D_F32, workspace, workspace_bytes, vertices, vertex_capacity, counts_host, stream);
+}
+
+p3d_status p3d_mc_count_typed(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, size_t workspace_bytes,
+                              float *vertices, int64_t vertex_capacity, int64_t *counts_host, void *stream) {
     p3d::McGeom g;
+    if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_count: unknown dtype");
     if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_count: invalid descriptor");
     if (!grid || !workspace || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_count: null pointer");
     if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_count: global_rx must be >= 1");
@@ -161,7 +167,7 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
 
     // header, the tile scan state and the chunk sums are contiguous: one memset
     P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
-    p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+    p3d::launch_tile_pass(grid, dtype, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
     if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_count: ") + p3d::tile_pass_error());
     P3D_CUDA(cudaGetLastError());
 
@@ -178,7 +184,13 @@ p3d_status p3d_mc_count(const p3d_mc_desc *desc, const float *grid, void *worksp
 
 p3d_status p3d_mc_vertices(const p3d_mc_desc *desc, const float *grid, void *workspace, float *vertices,
                            int64_t vertex_capacity, void *stream) {
+    return p3d_mc_vertices_typed(desc, grid, P3D_F32, workspace, vertices, vertex_capacity, stream);
+}
+
+p3d_status p3d_mc_vertices_typed(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, float *vertices,
+                                 int64_t vertex_capacity, void *stream) {
     p3d::McGeom g;
+    if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: unknown dtype");
     if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: invalid descriptor");
     if (!grid || !workspace || (!vertices && vertex_capacity > 0)) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: null pointer");
     if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_vertices: global_rx must be >= 1");
@@ -186,7 +198,7 @@ p3d_status p3d_mc_vertices(const p3d_mc_desc *desc, const float *grid, void *wor
     const p3d::McWorkspace ws = bind(workspace, l);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     P3D_CUDA(cudaMemsetAsync(&ws.header->ticket, 0, sizeof(unsigned int), s));
-    p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 1, s);
+    p3d::launch_tile_pass(grid, dtype, g, ws, make_params(desc, 0), vertices, vertex_capacity, 1, s);
     if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_vertices: ") + p3d::tile_pass_error());
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
@@ -216,7 +228,7 @@ p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *
     switch (stage) {
         case 0: P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s)); break;
         case 1:
-            p3d::launch_tile_pass(grid, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+            p3d::launch_tile_pass(grid, P3D_F32, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
             if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, p3d::tile_pass_error());
             break;
         default: return fail(P3D_ERR_INVALID, "p3d_mc_debug_stage: stage must be 0 or 1");

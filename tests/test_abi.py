@@ -20,6 +20,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ["p3d_mc_workspace_bytes", "p3d_mc_vertex_capacity_hint", "p3d_mc_count", "p3d_mc_vertices", "p3d_mc_faces",
+              "p3d_mc_count_typed", "p3d_mc_vertices_typed",
               "p3d_mc_run", "p3d_mc_plane_table_words", "p3d_mc_export_first_plane",
               "p3d_mc_import_halo_plane", "p3d_mt_classify", "p3d_mt_index", "p3d_mt_emit", "p3d_mt_backward",
               "p3d_last_error", "p3d_abi_version"]:
@@ -31,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/prim3d_b200.h but not exported"
-    assert capi.abi_version() == 2
+    assert capi.abi_version() == 3
 
 
 def test_workspace_size_is_a_few_bits_per_sample():

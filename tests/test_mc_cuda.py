@@ -123,6 +123,61 @@ def test_python_wrapper_contract():
         prim3d._C.marching_cubes(torch.zeros(8, 8, 16).cuda()[:, :, ::2], 0.0, [0, 0, 0], [8, 8, 8])
 
 
+DTYPE_GRIDS = {
+    # dtype: integer-valued or narrow-range grids whose float32 cast is not the identity where that is possible
+    "float16": lambda: (inputs.noise((19, 21, 140), 21) * 4).astype(np.float16),
+    "bfloat16": lambda: inputs.noise((19, 21, 140), 22),          # rounded to bf16 on the device below
+    "float64": lambda: inputs.noise((19, 21, 140), 23).astype(np.float64) * (1 + 2.0 ** -30) + 1e-9,
+    "int64": lambda: inputs.sphere_int64(72) * (2 ** 33 + 12345) + 1,  # |values| > 2^24: the cast rounds
+    "int32": lambda: (inputs.sphere_int64(40) * 1000003 + 7).astype(np.int32),
+    "int16": lambda: (inputs.noise((9, 40, 200), 24) * 3000).astype(np.int16),
+    "uint8": lambda: ((inputs.noise((33, 9, 130), 25) + 1) * 127).astype(np.uint8),
+}
+
+
+@pytest.mark.parametrize("name", list(DTYPE_GRIDS))
+def test_fused_dtype_ingest_equals_cast_then_run(name):
+    """Grids of other element types are converted to float32 on chip (p3d_mc_count_typed): every output must be
+    bit-identical to casting first (the reference wrapper's `.to(torch.float32)`, marching_cubes.py:86-87) --
+    through the C ABI, through prim3d.libPrim3D and through prim3d.marching_cubes, and equal to the oracle on
+    the cast grid."""
+    import prim3d
+    from primitive3d_b200 import capi
+    g = torch.from_numpy(np.ascontiguousarray(DTYPE_GRIDS[name]())).cuda()
+    if name == "bfloat16":
+        g = g.to(torch.bfloat16)
+    thresh = 100.0 if name == "uint8" else 0.0
+    cast = g.to(torch.float32)
+    v0, f0 = capi.marching_cubes(cast, thresh)
+    v1, f1 = capi.marching_cubes(g, thresh)
+    assert v1.dtype == torch.float32 and f1.dtype == torch.int32
+    assert torch.equal(v0.view(torch.int32), v1.view(torch.int32)) and torch.equal(f0, f1)
+    up = [float(s) for s in g.shape]
+    v2, f2 = prim3d._C.marching_cubes(g, thresh, [0.0, 0.0, 0.0], up)
+    assert torch.equal(v0.view(torch.int32), v2.view(torch.int32)) and torch.equal(f0, f2)
+    v3, f3 = prim3d.marching_cubes(g.cpu(), thresh)   # host tensor of the native dtype: transferred as it is
+    assert torch.equal(v0.view(torch.int32), v3.view(torch.int32)) and torch.equal(f0, f3)
+    # vertices-only second pass (capacity too small) reads the typed grid too
+    desc = capi.McDesc.make(g.shape, thresh)
+    V, F, ws, vbuf = capi.mc_count(desc, g, vertex_capacity=7)
+    v4 = capi.mc_vertices(desc, g, ws, V, vbuf)
+    assert torch.equal(v0.view(torch.int32), v4.view(torch.int32))
+    ov, of = mc.marching_cubes(cast.cpu().numpy(), thresh)
+    assert_same_mesh(v1.cpu().numpy(), f1.cpu().numpy(), ov, of, ordered_faces=True)
+    assert v1.shape[0] > 0
+
+
+def test_unsupported_dtype_is_cast_by_the_wrapper():
+    import prim3d
+    g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
+    v0, f0 = prim3d.marching_cubes(g, 0.0)
+    v1, f1 = prim3d.marching_cubes((g > 0).to(torch.int8) * 2 - 1, 0.0)   # int8 is not read directly
+    v2, f2 = prim3d.marching_cubes(((g > 0).to(torch.float32) * 2 - 1), 0.0)
+    assert torch.equal(v1, v2) and torch.equal(f1, f2) and f0.shape == f1.shape
+    with pytest.raises(RuntimeError, match="expected scalar type Float"):
+        prim3d._C.marching_cubes((g > 0).to(torch.int8), 0.0, [0, 0, 0], [12, 12, 12])
+
+
 def test_deterministic_and_misaligned_input():
     grid = inputs.noise((40, 48, 64), 21)
     a = run_capi(grid, 0.0, None, None)
