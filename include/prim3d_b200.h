@@ -136,6 +136,17 @@ p3d_status p3d_mc_vertices_typed(const p3d_mc_desc *desc, const void *grid, int 
 p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t *faces,
                         int64_t vertex_id_base, void *stream);
 
+/* Whole extraction with ONE host synchronisation (single GPU: owned_x == rx).  Both passes are
+ * queued back to back into buffers of speculative capacity; the host waits once, for {V, F}.
+ * vertices: float[3*vertex_capacity], faces: int32[3*face_capacity] (device).  On return
+ * counts_host = {V, F}; the vertex buffer is final iff V <= vertex_capacity (else call
+ * p3d_mc_vertices_typed with an exact buffer) and the face buffer is final iff F <=
+ * face_capacity (else nothing was written to it: call p3d_mc_faces with an exact buffer).
+ * The reference synchronises twice and allocates in between (marching_cubes.cu:251-263). */
+p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                          size_t workspace_bytes, float *vertices, int64_t vertex_capacity,
+                          int32_t *faces, int64_t face_capacity, int64_t *counts_host, void *stream);
+
 /* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
  * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: tile pass (classify,
  * count, look-back, vertices).  The face stage (scan over chunks + faces) is p3d_mc_faces itself. */

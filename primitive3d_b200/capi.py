@@ -64,6 +64,8 @@ def lib():
         L.p3d_mc_count_typed.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_vertices_typed.restype = ctypes.c_int
         L.p3d_mc_vertices_typed.argtypes = [dp, vp, ctypes.c_int, vp, vp, i64, vp]
+        L.p3d_mc_extract.restype = ctypes.c_int
+        L.p3d_mc_extract.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, i64, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_faces.restype = ctypes.c_int
         L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
@@ -163,6 +165,29 @@ def mc_faces(desc, workspace, F, vertex_id_base=0):
     with torch.cuda.device(workspace.device):
         check(lib().p3d_mc_faces(ctypes.byref(desc), workspace.data_ptr(), faces.data_ptr(), int(vertex_id_base), _stream()))
     return faces
+
+
+def mc_extract(desc, grid, vertex_capacity=None, face_capacity=None):
+    """Whole single-GPU extraction with one host synchronisation (p3d_mc_extract): both passes are queued into
+    buffers of speculative capacity (None = the library's vertex hint, twice that many faces); whatever did not
+    fit is redone into an exact buffer.  -> (vertices f32 [V,3], faces i32 [F,3], V, F)."""
+    dtype = _grid_ok(grid)
+    ws = torch.empty(mc_workspace_bytes(desc), dtype=torch.uint8, device=grid.device)
+    if vertex_capacity is None:
+        vertex_capacity = lib().p3d_mc_vertex_capacity_hint(ctypes.byref(desc))
+    if face_capacity is None:
+        face_capacity = 2 * int(vertex_capacity)
+    vbuf = torch.empty((int(vertex_capacity), 3), dtype=torch.float32, device=grid.device)
+    fbuf = torch.empty((int(face_capacity), 3), dtype=torch.int32, device=grid.device)
+    counts = (ctypes.c_int64 * 2)()
+    with torch.cuda.device(grid.device):
+        check(lib().p3d_mc_extract(ctypes.byref(desc), grid.data_ptr(), dtype, ws.data_ptr(), ws.numel(),
+                                   vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity),
+                                   fbuf.data_ptr() if face_capacity else None, int(face_capacity), counts, _stream()))
+    V, F = counts[0], counts[1]
+    verts = mc_vertices(desc, grid, ws, V, vbuf)
+    faces = fbuf[:F] if F <= face_capacity else mc_faces(desc, ws, F)
+    return verts, faces, V, F
 
 
 def marching_cubes(grid, thresh, lower=None, upper=None, vertex_capacity=None):

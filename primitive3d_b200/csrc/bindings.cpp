@@ -30,7 +30,7 @@ using torch::Tensor;
 #define P3D_CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")
 
 std::mutex g_capacity_mutex;
-std::map<std::array<int64_t, 3>, int64_t> g_last_vertex_count;  // grid shape -> V of its last extraction
+std::map<std::array<int64_t, 3>, std::array<int64_t, 2>> g_last_counts;  // grid shape -> {V, F} of its last extraction
 
 void check_status(p3d_status st, const char *what) {
     TORCH_CHECK(st == P3D_OK, what, " failed (status ", static_cast<int>(st), "): ", p3d_last_error());
@@ -86,43 +86,56 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
     TORCH_CHECK(ws_bytes > 0, "marching_cubes: invalid grid shape");
     Tensor workspace = torch::empty({static_cast<int64_t>(ws_bytes)}, bytes_opt);
 
-    // The vertices are written by the same pass that counts them (the grid is read once), so their buffer
-    // is sized before V is known: the previous V of this grid shape plus a margin if there is one, else the
-    // library's hint.  A too-small guess costs a second, vertices-only pass; nothing else depends on it.
+    // Both passes are queued before the host waits (one synchronisation; the reference has two with the
+    // allocations in between, marching_cubes.cu:251-263), so the output buffers are sized before V and F are
+    // known: the previous counts of this grid shape plus a margin if there are any, else the library's hint.
+    // A too-small guess costs a second, exact-size pass for that output; nothing else depends on it.
     const std::array<int64_t, 3> key = {desc.rx, desc.ry, desc.rz};
-    int64_t cap = p3d_mc_vertex_capacity_hint(&desc);
+    int64_t cap = p3d_mc_vertex_capacity_hint(&desc), fcap = 2 * cap;
     {
         std::lock_guard<std::mutex> lock(g_capacity_mutex);
-        auto it = g_last_vertex_count.find(key);
-        if (it != g_last_vertex_count.end()) cap = std::min<int64_t>(it->second + it->second / 16 + 4096, INT32_MAX);
+        auto it = g_last_counts.find(key);
+        if (it != g_last_counts.end()) {
+            cap = std::min<int64_t>(it->second[0] + it->second[0] / 16 + 4096, INT32_MAX);
+            fcap = it->second[1] + it->second[1] / 16 + 4096;
+        }
     }
     const auto f32_opt = density_grid.options().dtype(torch::kFloat);
+    const auto i32_opt = density_grid.options().dtype(torch::kInt);
     Tensor vbuf = torch::empty({cap, 3}, f32_opt);
+    Tensor fbuf = torch::empty({fcap, 3}, i32_opt);
 
     int64_t counts[2] = {0, 0};
-    check_status(p3d_mc_count_typed(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(), ws_bytes,
-                                    vbuf.data_ptr<float>(), cap, counts, stream),
-                 "p3d_mc_count");
+    check_status(p3d_mc_extract(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(), ws_bytes, vbuf.data_ptr<float>(),
+                                cap, fbuf.data_ptr<int32_t>(), fcap, counts, stream),
+                 "p3d_mc_extract");
     {
         std::lock_guard<std::mutex> lock(g_capacity_mutex);
-        if (g_last_vertex_count.size() > 64) g_last_vertex_count.clear();
-        g_last_vertex_count[key] = counts[0];
+        if (g_last_counts.size() > 64) g_last_counts.clear();
+        g_last_counts[key] = {counts[0], counts[1]};
     }
 
-    Tensor vertices;
+    // a view keeps the whole speculative buffer alive: copy out when most of it would be wasted
+    auto trimmed = [](const Tensor &buf, int64_t n, int64_t capacity) {
+        Tensor t = buf.narrow(0, 0, n);
+        const int64_t wasted = (capacity - n) * 12;
+        return wasted > std::max<int64_t>(int64_t(64) << 20, n * 12) ? t.clone() : t;
+    };
+    Tensor vertices, faces;
     if (counts[0] <= cap) {
-        vertices = vbuf.narrow(0, 0, counts[0]);
-        // a view keeps the whole speculative buffer alive: copy out when most of it would be wasted
-        const int64_t wasted = (cap - counts[0]) * 12;
-        if (wasted > std::max<int64_t>(int64_t(64) << 20, counts[0] * 12)) vertices = vertices.clone();
+        vertices = trimmed(vbuf, counts[0], cap);
     } else {
         vertices = torch::empty({counts[0], 3}, f32_opt);
         check_status(p3d_mc_vertices_typed(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(),
                                            vertices.data_ptr<float>(), counts[0], stream),
                      "p3d_mc_vertices");
     }
-    Tensor faces = torch::empty({counts[1], 3}, density_grid.options().dtype(torch::kInt));
-    check_status(p3d_mc_faces(&desc, workspace.data_ptr(), faces.data_ptr<int32_t>(), 0, stream), "p3d_mc_faces");
+    if (counts[1] <= fcap) {
+        faces = trimmed(fbuf, counts[1], fcap);
+    } else {
+        faces = torch::empty({counts[1], 3}, i32_opt);
+        check_status(p3d_mc_faces(&desc, workspace.data_ptr(), faces.data_ptr<int32_t>(), 0, stream), "p3d_mc_faces");
+    }
     // `workspace` is released to the caching allocator here; the allocator keeps it alive for the
     // kernels already queued on this stream.
     return {vertices, faces};

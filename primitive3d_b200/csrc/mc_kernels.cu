@@ -769,7 +769,10 @@ __device__ __forceinline__ uint32_t corner_code(const uint4 &w, const uint4 &n, 
 }
 
 __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
-    k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces) {
+    k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces, unsigned long long face_capacity) {
+    // speculative launch (p3d_mc_extract): the buffer was sized before F was known; if it is too small nothing is
+    // written and the caller runs the pass again with an exact buffer
+    if (ws.header->total_f > face_capacity) return;
     extern __shared__ __align__(16) unsigned char face_smem[];
     // per corner code: up to 15 entry nibbles, nibble 15 = #triangles
     uint64_t *s_table = reinterpret_cast<uint64_t *>(face_smem);
@@ -1190,7 +1193,8 @@ __global__ void __launch_bounds__(kRoundTiles) k_round_sums(McGeom g, McWorkspac
     }
 }
 
-void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s) {
+void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
+                  cudaStream_t s) {
     if (g.npieces <= 0) return;
     k_round_sums<<<(unsigned)g.nfrounds, kRoundTiles, 0, s>>>(g, ws);
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
@@ -1201,7 +1205,8 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     }();
     (void)attr;
     cudaMemsetAsync(&ws.header->ticket_faces, 0, sizeof(unsigned int), s);
-    k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces);
+    k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces,
+                                                                                         (unsigned long long)face_capacity);
 }
 
 // Multi-GPU.  Export: the first plane's table entries (shard-local ids).  Import: install the next shard's

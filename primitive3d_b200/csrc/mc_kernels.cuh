@@ -97,7 +97,9 @@ struct McEmitParams {
 // dtype: p3d_dtype of the grid's elements (include/prim3d_b200.h); every sample is converted to float32 on chip.
 void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
                       float *verts, int64_t vertex_capacity, int mode, cudaStream_t s);
-void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, cudaStream_t s);
+// face_capacity: faces the buffer holds; the pass writes nothing if the workspace's F exceeds it
+void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
+                  cudaStream_t s);
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor

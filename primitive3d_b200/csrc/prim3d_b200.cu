@@ -213,8 +213,42 @@ p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t 
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
     p3d::McEmitParams prm = make_params(desc, vertex_id_base);
-    p3d::launch_faces(g, ws, prm, faces, static_cast<cudaStream_t>(stream));
+    p3d::launch_faces(g, ws, prm, faces, INT64_MAX, static_cast<cudaStream_t>(stream));
     P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, size_t workspace_bytes,
+                          float *vertices, int64_t vertex_capacity, int32_t *faces, int64_t face_capacity,
+                          int64_t *counts_host, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_extract: invalid descriptor");
+    if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_extract: unknown dtype");
+    if (!grid || !workspace || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_extract: null pointer");
+    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_extract: global_rx must be >= 1");
+    if (desc->rx != desc->owned_x) return fail(P3D_ERR_INVALID, "p3d_mc_extract: a slab with a halo plane needs the staged calls");
+    if (vertex_capacity < 0 || (vertex_capacity > 0 && !vertices) || face_capacity < 0 || (face_capacity > 0 && !faces))
+        return fail(P3D_ERR_INVALID, "p3d_mc_extract: capacity without a buffer");
+    const Layout l = make_layout(g);
+    if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_extract: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_extract: workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const p3d::McWorkspace ws = bind(workspace, l);
+
+    // everything is queued before the host waits: the face pass starts the moment the tile pass ends
+    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
+    p3d::launch_tile_pass(grid, dtype, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+    if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_extract: ") + p3d::tile_pass_error());
+    if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, s);
+    P3D_CUDA(cudaGetLastError());
+    int64_t *pin = pinned_counts();
+    int64_t *dst = pin ? pin : counts_host;
+    P3D_CUDA(cudaMemcpyAsync(dst, &ws.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaStreamSynchronize(s));
+    counts_host[0] = dst[0];
+    counts_host[1] = dst[1];
+    if (counts_host[0] > INT32_MAX)
+        return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract: vertex count exceeds the int32 face-index contract");
     return P3D_OK;
 }
 

@@ -54,6 +54,7 @@ def gather_counts(V, F, device, group=None):
 
 
 _last_vertex_count = {}   # slab shape -> V of its last extraction (sizes the speculative vertex buffer)
+_last_face_count = {}     # slab shape -> F of its last extraction (single GPU: sizes the speculative face buffer)
 
 
 def capacity_for(shape):
@@ -92,13 +93,22 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
 
     if vertex_capacity is None:
         vertex_capacity = capacity_for(slab.shape)
+    key = tuple(int(s) for s in slab.shape)
+    if world == 1:
+        # one GPU: nothing to exchange, so both passes are queued at once and the host waits a single time
+        f_prev = _last_face_count.get(key)
+        f_cap = None if f_prev is None else f_prev + f_prev // 16 + 4096
+        verts, faces, V, F = capi.mc_extract(desc, slab, vertex_capacity, f_cap)
+        if len(_last_vertex_count) > 64:
+            _last_vertex_count.clear()
+            _last_face_count.clear()
+        _last_vertex_count[key], _last_face_count[key] = V, F
+        return SlabMesh(verts, faces, 0, 0, V, F)
     V, F, ws, vbuf = capi.mc_count(desc, slab, vertex_capacity=vertex_capacity)
     if len(_last_vertex_count) > 64:
         _last_vertex_count.clear()
     _last_vertex_count[tuple(int(s) for s in slab.shape)] = V
     verts = capi.mc_vertices(desc, slab, ws, V, vbuf)   # local: needs nothing from the other ranks
-    if world == 1:
-        return SlabMesh(verts, capi.mc_faces(desc, ws, F, 0), 0, 0, V, F)
 
     L = capi.lib()
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -167,6 +167,22 @@ def test_fused_dtype_ingest_equals_cast_then_run(name):
     assert v1.shape[0] > 0
 
 
+@pytest.mark.parametrize("name", ["gyroid128", "noise65_s2", "bounds_asym", "empty", "min222"])
+def test_single_sync_extraction_equals_staged_calls(name):
+    """p3d_mc_extract queues both passes into speculative buffers and waits once; whatever the capacities, the
+    outputs equal those of p3d_mc_count + p3d_mc_vertices + p3d_mc_faces."""
+    from primitive3d_b200 import capi
+    factory, thresh, lower, upper = CASES[name]
+    g = torch.from_numpy(np.ascontiguousarray(factory())).cuda()
+    v0, f0 = capi.marching_cubes(g, thresh, lower, upper)
+    desc = capi.McDesc.make(g.shape, thresh, lower, upper)
+    V0, F0 = v0.shape[0], f0.shape[0]
+    for vcap, fcap in [(None, None), (V0, F0), (V0 + 9, F0 + 9), (max(V0 - 1, 0), F0), (V0, max(F0 - 1, 0)), (3, 5), (0, 0)]:
+        v, f, V, F = capi.mc_extract(desc, g, vcap, fcap)
+        assert (V, F) == (V0, F0)
+        assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0), (vcap, fcap)
+
+
 def test_unsupported_dtype_is_cast_by_the_wrapper():
     import prim3d
     g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
