@@ -53,6 +53,22 @@ def gather_counts(V, F, device, group=None):
     return [tuple(r) for r in out.view(world, 2).cpu().tolist()]
 
 
+def exchange_counts_and_tables(V, F, table, group=None):
+    """ONE all-gather per extraction: every rank contributes its first-plane piece table (int32 [words], on the
+    compute device for NCCL, CPU for gloo) with its {V, F} appended as two int64.  Returns (counts as a list of
+    (V_r, F_r), tables int32 [world, words]).  Reading the counts back is the only synchronisation."""
+    world = dist.get_world_size(group)
+    words = table.numel()
+    mine = torch.empty(words + 4, dtype=torch.int32, device=table.device)
+    mine[:words] = table
+    mine[words:] = torch.tensor([int(V), int(F)], dtype=torch.int64).view(torch.int32).to(table.device, non_blocking=True)
+    out = torch.empty(world * (words + 4), dtype=torch.int32, device=table.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    out = out.view(world, words + 4)
+    counts = out[:, words:].contiguous().view(torch.int64).cpu().tolist()
+    return [tuple(c) for c in counts], out[:, :words]
+
+
 _last_vertex_count = {}   # slab shape -> V of its last extraction (sizes the speculative vertex buffer)
 _last_face_count = {}     # slab shape -> F of its last extraction (single GPU: sizes the speculative face buffer)
 
@@ -112,20 +128,17 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
 
     L = capi.lib()
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    counts = gather_counts(V, F, slab.device, group)
-    v_off, f_off, v_tot, f_tot = exclusive_offsets(counts, rank)
-    if v_tot > 2 ** 31 - 1:
-        raise OverflowError("global vertex count exceeds the int32 face-index contract")
-
-    # numbering of the boundary plane: everybody publishes the piece table of its first plane
+    # numbering of the boundary plane: everybody publishes the piece table of its first plane, and its counts
+    # ride along in the same all-gather
     words = L.p3d_mc_plane_table_words(ctypes.byref(desc))
     table = torch.empty(words, dtype=torch.int32, device=slab.device)
     capi.check(L.p3d_mc_export_first_plane(ctypes.byref(desc), ws.data_ptr(), table.data_ptr(), stream))
-    tables = torch.empty(world * words, dtype=torch.int32, device=slab.device)
-    dist.all_gather_into_tensor(tables, table, group=group)
-    tables = tables.view(world, words)
+    counts, tables = exchange_counts_and_tables(V, F, table, group)
+    v_off, f_off, v_tot, f_tot = exclusive_offsets(counts, rank)
+    if v_tot > 2 ** 31 - 1:
+        raise OverflowError("global vertex count exceeds the int32 face-index contract")
     if rank + 1 < world:
-        capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(desc), ws.data_ptr(), tables[rank + 1].data_ptr(), int(V),
-                                              stream))
+        nxt = tables[rank + 1].contiguous()
+        capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(desc), ws.data_ptr(), nxt.data_ptr(), int(V), stream))
     faces = capi.mc_faces(desc, ws, F, v_off)
     return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)

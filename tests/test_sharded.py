@@ -58,6 +58,10 @@ def test_count_exchange_world_size_2_gloo():
     outs.sort(key=lambda o: o["rank"])
     assert outs[0]["counts"] == outs[1]["counts"] == [[100, 1000], [101, 1010]]
     assert outs[0]["offsets"] == [0, 0, 201, 2010] and outs[1]["offsets"] == [100, 1000, 201, 2010]
+    # the fused exchange: tables of every rank + 64-bit counts in one all-gather
+    for o in outs:
+        assert o["counts2"] == [[2 ** 33, 2 ** 40], [2 ** 33 + 1, 2 ** 40 + 10]]
+        assert o["tables"] == [list(range(24)), [1000 + i for i in range(24)]]
 
 
 @pytest.mark.gpu
