@@ -225,6 +225,19 @@ p3d_status p3d_mt_backward(const float *points, const float *sdf, const int64_t 
                            int64_t num_vertices, const float *grad_verts, float *grad_points,
                            float *grad_sdf, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Binary PLY body, assembled on the device.
+ * Replaces the per-vertex / per-face ofstream.write loops of prim3d::save_mesh_as_ply,
+ * src/prim3d/Utility/marching_cubes.cu:333-349 (same bytes): vertex_records receives
+ * num_vertices records of 15 bytes {float x, y, z; uchar r, g, b} (buffer of 15*num_vertices
+ * bytes rounded up to a multiple of 4, 4-byte aligned), face_records num_faces records of
+ * 16 bytes {int32 3, a, b, c} (16-byte aligned).  All pointers are device pointers;
+ * asynchronous on `stream`.
+ * ---------------------------------------------------------------------------------------- */
+p3d_status p3d_ply_pack(const float *vertices, const uint8_t *colors, int64_t num_vertices,
+                        const int32_t *faces, int64_t num_faces, void *vertex_records,
+                        void *face_records, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

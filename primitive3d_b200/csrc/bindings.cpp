@@ -143,17 +143,18 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
 
 // prim3d::save_mesh_as_ply, marching_cubes.cu:307-352: same binary-little-endian PLY bytes
 // (header text, 15-byte vertex records x,y,z,r,g,b, faces as int32 [3,a,b,c]), assembled in one
-// buffer and written with a single call instead of one ofstream.write per vertex.
+// buffer and written with a single call instead of one ofstream.write per vertex.  A mesh that
+// lives on a CUDA device has its two record sections packed there (p3d_ply_pack) and copied once
+// each, straight to their place behind the header.
 void save_mesh_as_ply(const std::string filename, Tensor vertices, Tensor faces, Tensor colors) {
     P3D_CHECK_CONTIGUOUS(vertices);
     P3D_CHECK_CONTIGUOUS(faces);
     P3D_CHECK_CONTIGUOUS(colors);
-    vertices = vertices.to(torch::kCPU);
-    faces = faces.to(torch::kCPU);
-    colors = colors.to(torch::kCPU);
     TORCH_CHECK(vertices.scalar_type() == torch::kFloat, "vertices must be float32");
     TORCH_CHECK(faces.scalar_type() == torch::kInt, "faces must be int32");
     TORCH_CHECK(colors.scalar_type() == torch::kByte, "colors must be uint8");
+    TORCH_CHECK(vertices.dim() == 2 && vertices.size(1) == 3 && faces.dim() == 2 && faces.size(1) == 3 &&
+                colors.numel() == vertices.numel(), "expected vertices [V,3], faces [F,3], colors [V,3]");
 
     const int64_t nv = vertices.size(0), nf = faces.size(0);
     std::string buf = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(nv) +
@@ -164,17 +165,35 @@ void save_mesh_as_ply(const std::string filename, Tensor vertices, Tensor faces,
     const size_t head = buf.size();
     buf.resize(head + static_cast<size_t>(nv) * 15 + static_cast<size_t>(nf) * 16);
     char *out = &buf[head];
-    const float *v = vertices.data_ptr<float>();
-    const uint8_t *c = colors.data_ptr<uint8_t>();
-    for (int64_t i = 0; i < nv; ++i, out += 15) {
-        std::memcpy(out, v + 3 * i, 12);
-        std::memcpy(out + 12, c + 3 * i, 3);
-    }
-    const int32_t *f = faces.data_ptr<int32_t>();
-    const int32_t three = 3;
-    for (int64_t i = 0; i < nf; ++i, out += 16) {
-        std::memcpy(out, &three, 4);
-        std::memcpy(out + 4, f + 3 * i, 12);
+    if (vertices.is_cuda() && nv + nf > 0) {
+        const c10::cuda::CUDAGuard guard(vertices.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        faces = faces.to(vertices.device());
+        colors = colors.to(vertices.device());
+        const auto bytes_opt = torch::TensorOptions().dtype(torch::kUInt8).device(vertices.device());
+        Tensor vrec = torch::empty({(nv * 15 + 3) / 4 * 4}, bytes_opt), frec = torch::empty({nf * 16}, bytes_opt);
+        check_status(p3d_ply_pack(vertices.data_ptr<float>(), colors.data_ptr<uint8_t>(), nv, faces.data_ptr<int32_t>(), nf,
+                                  vrec.data_ptr(), frec.data_ptr(), stream),
+                     "p3d_ply_pack");
+        if (nv) C10_CUDA_CHECK(cudaMemcpyAsync(out, vrec.data_ptr(), static_cast<size_t>(nv) * 15, cudaMemcpyDeviceToHost, stream));
+        if (nf) C10_CUDA_CHECK(cudaMemcpyAsync(out + nv * 15, frec.data_ptr(), static_cast<size_t>(nf) * 16, cudaMemcpyDeviceToHost, stream));
+        C10_CUDA_CHECK(cudaStreamSynchronize(stream));
+    } else {
+        vertices = vertices.to(torch::kCPU);
+        faces = faces.to(torch::kCPU);
+        colors = colors.to(torch::kCPU);
+        const float *v = vertices.data_ptr<float>();
+        const uint8_t *c = colors.data_ptr<uint8_t>();
+        for (int64_t i = 0; i < nv; ++i, out += 15) {
+            std::memcpy(out, v + 3 * i, 12);
+            std::memcpy(out + 12, c + 3 * i, 3);
+        }
+        const int32_t *f = faces.data_ptr<int32_t>();
+        const int32_t three = 3;
+        for (int64_t i = 0; i < nf; ++i, out += 16) {
+            std::memcpy(out, &three, 4);
+            std::memcpy(out + 4, f + 3 * i, 12);
+        }
     }
     std::FILE *fp = std::fopen(filename.c_str(), "wb");
     TORCH_CHECK(fp != nullptr, "cannot open ", filename);

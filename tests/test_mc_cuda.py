@@ -183,6 +183,32 @@ def test_single_sync_extraction_equals_staged_calls(name):
         assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0), (vcap, fcap)
 
 
+@pytest.mark.parametrize("nv,nf", [(0, 0), (1, 0), (3, 1), (1001, 333), (4096, 8190)])
+def test_ply_assembled_on_the_device_has_the_same_bytes(tmp_path, nv, nf):
+    """save_mesh on CUDA tensors packs the 15-byte vertex and 16-byte face records on the device (p3d_ply_pack);
+    the file must equal the one written from host tensors, i.e. the reference's layout (marching_cubes.cu:307-352)."""
+    import prim3d
+    rng = np.random.default_rng(nv * 7 + nf)
+    v = torch.from_numpy(rng.standard_normal((nv, 3)).astype(np.float32))
+    f = torch.from_numpy(rng.integers(0, max(nv, 1), (nf, 3)).astype(np.int32))
+    c = torch.from_numpy(rng.integers(0, 256, (nv, 3)).astype(np.uint8))
+    a, b = str(tmp_path / "host.ply"), str(tmp_path / "device.ply")
+    prim3d.save_mesh(v, f, c, filename=a)
+    prim3d.save_mesh(v.cuda(), f.cuda(), c.cuda(), filename=b)
+    raw = open(a, "rb").read()
+    assert raw == open(b, "rb").read()
+    body = raw[raw.index(b"end_header\n") + 11:]
+    assert len(body) == 15 * nv + 16 * nf
+    rec = np.frombuffer(body[:15 * nv], np.uint8).reshape(nv, 15)
+    assert np.array_equal(rec[:, :12].copy().view(np.float32).reshape(nv, 3), v.numpy()) and np.array_equal(rec[:, 12:], c.numpy())
+    fr = np.frombuffer(body[15 * nv:], np.int32).reshape(nf, 4)
+    assert (fr[:, 0] == 3).all() and np.array_equal(fr[:, 1:], f.numpy())
+    # default colours (127) with a mesh that is still on the device
+    prim3d.save_mesh(v.cuda(), f.cuda().long(), filename=b)
+    prim3d.save_mesh(v, f.long(), filename=a)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 def test_unsupported_dtype_is_cast_by_the_wrapper():
     import prim3d
     g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
