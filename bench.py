@@ -40,6 +40,18 @@ KNOWN = {1024: (40621056, 81103132), 2048: (162441216, 324595996), 512: (1011148
          256: (2500608, 4972828), 128: (635904, 1261852)}
 
 
+def ncu_traffic(kernel, n):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_report.py); None if there is none."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        if rec.get("grid") == n:
+            return rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -318,7 +330,9 @@ def main():
     dom = max(k_ms, key=k_ms.get)
     line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "faces": "k_faces"}[dom],
                         "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": kernels[dom]["achieved_gbs"] / peak,
+                        "traffic": ncu_traffic({"tile_pass": "k_tile", "faces": "k_faces"}[dom], n) if world == 1 else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": k_bytes[dom], "launch_ms": k_ms[dom]}
     line["kernels"] = kernels
     line["host_overhead_ms_per_step"] = ms - sum(k_ms.values()) if world == 1 else None

@@ -12,21 +12,6 @@
 #include "mc_case_table.h"
 #include "scan_utils.cuh"
 
-#ifndef P3D_VERT_COMP
-#define P3D_VERT_COMP 0
-#endif
-#ifndef P3D_TILE_PREFETCH
-#define P3D_TILE_PREFETCH 0
-#endif
-#ifndef P3D_FACE_IDX
-#define P3D_FACE_IDX 0
-#endif
-#ifndef P3D_BITS_WORD
-#define P3D_BITS_WORD 1
-#endif
-#ifndef P3D_COUNT_EULER
-#define P3D_COUNT_EULER 1
-#endif
 
 namespace p3d {
 
@@ -99,13 +84,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
-}
-
-// L2 prefetch of the same box (no shared-memory destination, no completion tracking).
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -207,8 +185,8 @@ struct TileSmem {
     uint16_t nfp[kTileX * kTileY];  // triangles of each owned (row, piece)
     float dt[kRing];       // pending vertices: interpolation parameter ...
     uint16_t ent[kRing];   // ... and edge (axis<<13 | row<<7 | z)
-    int8_t ntri[256];      // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1: #triangles of the
-                           // case, or (P3D_COUNT_EULER) its correction  #triangles - (#crossed edges - 2)
+    int8_t ntri[256];      // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1:
+                           // the case's correction  #triangles - (#crossed edges - 2)
     PendingTile q[kQueue];
     unsigned long long bar;
     unsigned long long base;       // result of warp 0's non-blocking look-back at the top of an iteration
@@ -242,16 +220,12 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
                             ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
         const int nt = (int)(c_case_table[cs] >> 60);
-#if P3D_COUNT_EULER
         // crossed edges of the case, cube edges in the numbering of marching_cubes.cu:178-192
         const int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
         int ne = 0;
 #pragma unroll
         for (int e = 0; e < 12; ++e) ne += (int)(((cs >> ea[e]) ^ (cs >> eb[e])) & 1u);
         S.ntri[c] = (int8_t)(ne ? nt - (ne - 2) : 0);
-#else
-        S.ntri[c] = (int8_t)nt;
-#endif
     }
 
     // Tile id -> coordinates.  Tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
@@ -346,36 +320,12 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t start = S.q[slot].start, count = S.q[slot].count;
         uint4 *const te = table_entry(c);
         const uint4 tv = load_entry(te);
-#if P3D_VERT_COMP
-        // a lane per output float: consecutive lanes write consecutive words (12-byte vertices would make every
-        // store instruction touch three times the sectors it fills)
-        {
-            const int z0 = c.z * kTileZ;
-            float *const out = verts + base * 3ull;
-            for (uint32_t k = tid; k < 3u * count; k += kTileThreads) {
-                const uint32_t v = (k * 0xAAABu) >> 17, cc = k - 3u * v;  // k / 3, k % 3 (k < 2^16)
-                uint32_t idx = start + v;
-                if (idx >= (uint32_t)kRing) idx -= kRing;
-                if (base + v < vcap) {
-                    const uint32_t ent = S.ent[idx];
-                    const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
-                    const int ip = cc == 0 ? xg0 + c.x + (int)(er >> 3) : (cc == 1 ? c.y + (int)(er & 7u) : z0 + (int)ez);
-                    float pp = (float)ip;  // static_cast<float>(x), :107
-                    if (ax == cc) pp = __fadd_rn(pp, S.dt[idx]);
-                    const float sc = cc == 0 ? prm.scale[0] : (cc == 1 ? prm.scale[1] : prm.scale[2]);
-                    const float of = cc == 0 ? prm.offset[0] : (cc == 1 ? prm.offset[1] : prm.offset[2]);
-                    out[k] = __fadd_rn(__fmul_rn(pp, sc), of);  // two separately rounded ops (:298)
-                }
-            }
-        }
-#else
         for (uint32_t k = tid; k < count; k += kTileThreads) {
             uint32_t idx = start + k;
             if (idx >= (uint32_t)kRing) idx -= kRing;
             const unsigned long long id = base + k;
             if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
         }
-#endif
         finish_entry(te, tv, c, base, count);
         ring_used -= count;
         q_head = (q_head + 1) % kQueue;
@@ -437,7 +387,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // ---- phase 1: inside bits of the 81 staged rows.  inside = value > thresh (:25,31,37,43,50-57).
         // Samples outside the grid are staged as 0.0f; their bits take part in no mask that is not cut by a
         // validity test below, so they need no cleaning here. ----
-#if P3D_BITS_WORD
         {
             // a thread per (staged row, word): the eight lanes of a quarter warp read eight consecutive rows at the
             // same word, i.e. eight different 16-byte bank groups (a staged row is 33 x 16 bytes)
@@ -451,36 +400,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
             }
         }
-#else
-        {
-            auto row_bits = [&](int row) {
-                const float *src = tf + row * kBoxZ + lane;
-                const float f0 = src[0], f1 = src[32], f2 = src[64], f3 = src[96];
-                const uint32_t b0 = __ballot_sync(kFull, f0 > thresh), b1 = __ballot_sync(kFull, f1 > thresh);
-                const uint32_t b2 = __ballot_sync(kFull, f2 > thresh), b3 = __ballot_sync(kFull, f3 > thresh);
-                if (lane == 0) *reinterpret_cast<uint4 *>(&S.sbits[row * kSbitsStride]) = make_uint4(b0, b1, b2, b3);
-            };
-#pragma unroll
-            for (int bx = 0; bx <= kTileX; ++bx) row_bits(bx * kRowPitch + warp);  // rows (bx, yi = warp)
-            row_bits(warp * kRowPitch + kTileY);                                    // rows (bx = warp, yi = 8)
-            if (warp == 0) row_bits(kTileX * kRowPitch + kTileY);                   // row (8, 8)
-            // the halo sample (z0 + 128) of every staged row: a lane per row
-            if (warp >= 1 && warp <= 3) {
-                const int row = (warp - 1) * 32 + lane;
-                if (row < kBoxRows) S.sbits[row * kSbitsStride + 4] = tf[row * kBoxZ + kTileZ] > thresh ? 1u : 0u;
-            }
-        }
-#endif
         __syncthreads();  // [bits]
-#if P3D_TILE_PREFETCH
-        // the next tile's box is pulled into L2 now, so that the TMA load issued when the stage is free lands fast
-        int4 nc = make_int4(0, 0, 0, 0);
-        if (tid == 32) {
-            nc = locate(next_tile);
-            S.coord[(it + 1u) & 1u] = nc;
-            if (TMA && (uint32_t)nc.w < ntiles) tma_prefetch_3d(&tmap, nc.z * kTileZ, nc.y, nc.x);
-        }
-#endif
 
         // ---- phase 2: crossing masks and counts of my word ----
         const int x = x0 + xi, y = y0 + yi;
@@ -496,7 +416,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t m1 = hy ? (A ^ D) : 0u;            // +y edges, :35-39 / :113-124
         const uint32_t m2 = own ? ((A ^ A2) & zv) : 0u;   // +z edges, :41-45 / :126-137
         uint32_t nf = 0;
-#if P3D_COUNT_EULER
         // Triangles of my 32 cells without walking them.  Every row of the case table triangulates the closed
         // loops the surface cuts through the cell, a loop over k crossed edges into k - 2 triangles, so a cell
         // with E crossed edges and L loops has E - 2 L triangles (checked for all 256 cases, tests/test_tables.py).
@@ -527,19 +446,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             }
             nf = (uint32_t)total;
         }
-#else
-        if (hc) {                                         // cells with mixed corners, :48-66
-            const uint32_t B2 = __funnelshift_r(B, Bn, 1), C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
-            const uint32_t any = A | B | C | D | A2 | B2 | C2 | D2, all = A & B & C & D & A2 & B2 & C2 & D2;
-            for (uint32_t rem = (any & ~all) & zv; rem;) {
-                const int i = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const uint32_t code = (__funnelshift_r(A, An, i) & 3u) | ((__funnelshift_r(B, Bn, i) & 3u) << 2) |
-                                      ((__funnelshift_r(C, Cn, i) & 3u) << 4) | ((__funnelshift_r(D, Dn, i) & 3u) << 6);
-                nf += S.ntri[code];
-            }
-        }
-#endif
         // my (row, piece) = 4 adjacent lanes: packed {nx, ny, nz} (8-bit fields, <= 128 each)
         const uint32_t cnt = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 8) | ((uint32_t)__popc(m2) << 16);
         uint32_t inc = cnt;
@@ -567,6 +473,10 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * bstride + 4 * p + (tid & 3)] =
                     S.sbits[(kTileX * kRowPitch + (tid >> 2)) * kSbitsStride + (tid & 3)];
         }
+        // the look-back result of the top of this iteration: written by warp 0 before [bits], read here, and not
+        // overwritten before warp 0 has passed [count]
+        bool probe_ok = q_count && S.base_ok;
+        const unsigned long long probe_base = S.base;
         __syncthreads();  // [count]
 
         // ---- tile scan (every warp redundantly): first vertex of each (row, piece), relative to the tile ----
@@ -619,10 +529,6 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t first[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
         const uint32_t wmask[3] = {m0, m1, m2};
         const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
-        // the look-back result of the top of this iteration (read before warp 0 can overwrite it)
-        bool probe_ok = q_count && S.base_ok;
-        const unsigned long long probe_base = S.base;
-
         if (vt <= (uint32_t)kRing) {
             // ---- make room in the ring (rare): retire the oldest pending tiles, waiting for their ids ----
             while (q_count && (ring_used + vt > (uint32_t)kRing || q_count == (uint32_t)kQueue)) {
@@ -696,13 +602,11 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             ring_tail = 0;
         }
         // the next tile's coordinates are published before the barrier, its load is issued after it
-#if !P3D_TILE_PREFETCH
         int4 nc = make_int4(0, 0, 0, 0);
         if (tid == 32) {
             nc = locate(next_tile);
             S.coord[(it + 1u) & 1u] = nc;
         }
-#endif
         __syncthreads();  // [stage free]
         if (tid == 32) issue(nc);
 
@@ -941,9 +845,8 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                 const uint32_t zv = low_mask(rz - 1 - (p_ld * kTileZ + 32 * (2 * h + w)));
                 m[0] = A[w] ^ B[w], m[1] = A[w] ^ D[w], m[2] = (A[w] ^ A2) & zv, m[3] = B[w] ^ C[w];
                 m[4] = (B[w] ^ B2) & zv, m[5] = D[w] ^ C[w], m[6] = (D[w] ^ D2) & zv, m[7] = (C[w] ^ C2) & zv;
-                const uint32_t any = A[w] | B[w] | C[w] | D[w] | A2 | B2 | C2 | D2;
-                const uint32_t all = A[w] & B[w] & C[w] & D[w] & A2 & B2 & C2 & D2;
-                act = nf ? ((any & ~all) & zv) : 0u;  // :154,168-176
+                // mixed corners (:154,168-176) <=> one of the bottom x/y edges or of the four z edges is crossed
+                act = nf ? (((m[0] | m[1] | m[2]) | (m[3] | m[4] | m[5]) | (m[6] | m[7])) & zv) : 0u;
             };
             uint32_t run[8] = {ta.x, ta.y, ta.z, tb.y, tb.z, td.x, td.z, tcc.z};
             // crossings of the first half's two words per mask (8-bit fields): the second half starts after them
@@ -1028,17 +931,6 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                     __syncwarp();
                     // one triangle per lane: rank its three edges, 12-byte stores (:194-208)
                     int32_t *const out0 = faces + frun * 3ull;
-#if P3D_FACE_IDX
-                    // one face index per lane: consecutive lanes write consecutive words
-                    for (uint32_t j = lane; j < 3u * btot; j += 32) {
-                        const uint32_t t = (j * 0xAAABu) >> 17, cc = j - 3u * t;  // j / 3, j % 3
-                        const uint32_t ent = sc.tri[t];
-                        const uint32_t nib = ent >> (12u + 4u * cc);
-                        const uint2 en = sc.rank[((ent >> 5) & 63u) * kRankStride + (nib & 7u)];
-                        const uint32_t below = (((nib & 8u) ? 2u : 1u) << (ent & 31u)) - 1u;  // bits below z / below z+1
-                        out0[j] = (int32_t)(en.y + __popc(en.x & below));
-                    }
-#else
                     for (uint32_t j = lane; j < btot; j += 32) {
                         const uint32_t ent = sc.tri[j];
                         const uint32_t i = ent & 31u;
@@ -1052,7 +944,6 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                             out[cc] = (int32_t)(en.y + __popc(en.x & ((nib & 8u) ? below1 : below0)));
                         }
                     }
-#endif
                     __syncwarp();
                     frun += btot;
                 }
