@@ -358,6 +358,32 @@ def main():
             except Exception as exc:  # the comparison is informative only
                 line["reference_cuda_gyroid512"] = {"error": str(exc)[:200]}
 
+        # ---- the multi-GPU workload (gyroid 2048^3) on this single GPU: the base of the strong-scaling claim ----
+        try:
+            torch.cuda.empty_cache()
+            n2 = 2048
+            big = torch.empty((n2, n2, n2), dtype=torch.float32, device=dev)
+            for xs in range(0, n2, 256):
+                big[xs:xs + 256] = gyroid_cuda(n2, xs, xs + 256, dev)
+            for _ in range(2):
+                o2 = sharded.marching_cubes_slab(big, 0.0, 0, n2)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                o2 = sharded.marching_cubes_slab(big, 0.0, 0, n2)
+            b.record()
+            torch.cuda.synchronize()
+            ms2 = a.elapsed_time(b) / 5
+            assert (o2.num_vertices_total, o2.num_faces_total) == KNOWN[n2]
+            line["single_gpu_gyroid2048"] = {"ms_per_step": ms2, "value": n2 ** 3 / (ms2 * 1e-3) / 1e9, "unit": "Gvoxel/s",
+                                             "note": "configs[4] on one GPU: divide the N-GPU ms_per_step into this for "
+                                                     "the strong-scaling factor"}
+            del big, o2
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            line["single_gpu_gyroid2048"] = {"error": str(exc)[:200]}
+
         # ---- CPU baseline on a bounded sample ----
         line["cpu_baseline"] = cpu_baseline_pymcubes(n, args.sample_planes or 256)
     else:

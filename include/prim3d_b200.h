@@ -164,6 +164,23 @@ p3d_status p3d_mc_export_first_plane(const p3d_mc_desc *desc, const void *worksp
 p3d_status p3d_mc_import_halo_plane(const p3d_mc_desc *desc, void *workspace,
                                     const uint32_t *table_in, int64_t delta, void *stream);
 
+/* The same exchange without a host round trip between the two passes (the multi-GPU driver's fast
+ * path: tile pass, exchange, face pass are all queued; the host waits once, for the gathered counts):
+ *   p3d_mc_tile_async()       p3d_mc_count without the readback / synchronise;
+ *   p3d_mc_export_exchange()  out = uint32[p3d_mc_exchange_words(desc)]: the first-plane table followed by
+ *                             this shard's {V, F} as two int64 -- the all-gather payload of one shard;
+ *   p3d_mc_faces_exchanged()  gathered = the all-gather of every shard's payload, in rank order: computes
+ *                             this shard's vertex_id_base (sum of the lower shards' V), installs the next
+ *                             shard's table as the halo-plane numbering (shifted by this shard's V) and runs
+ *                             the face pass into `faces` (capacity as in p3d_mc_extract: nothing is written
+ *                             if F exceeds it).  All on the device, asynchronous. */
+p3d_status p3d_mc_tile_async(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                             size_t workspace_bytes, float *vertices, int64_t vertex_capacity, void *stream);
+int64_t p3d_mc_exchange_words(const p3d_mc_desc *desc);
+p3d_status p3d_mc_export_exchange(const p3d_mc_desc *desc, const void *workspace, uint32_t *out, void *stream);
+p3d_status p3d_mc_faces_exchanged(const p3d_mc_desc *desc, void *workspace, const uint32_t *gathered, int rank,
+                                  int world, int32_t *faces, int64_t face_capacity, void *stream);
+
 /* One-shot convenience for C/C++ callers: workspace and a vertex buffer of
  * p3d_mc_vertex_capacity_hint() through the callback, count, faces (and an exact vertex buffer
  * + p3d_mc_vertices if the hint was too small).  alloc(ctx, bytes) must return device memory on

@@ -66,6 +66,14 @@ def lib():
         L.p3d_mc_vertices_typed.argtypes = [dp, vp, ctypes.c_int, vp, vp, i64, vp]
         L.p3d_mc_extract.restype = ctypes.c_int
         L.p3d_mc_extract.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, i64, vp, i64, ctypes.POINTER(i64), vp]
+        L.p3d_mc_tile_async.restype = ctypes.c_int
+        L.p3d_mc_tile_async.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, i64, vp]
+        L.p3d_mc_exchange_words.restype = i64
+        L.p3d_mc_exchange_words.argtypes = [dp]
+        L.p3d_mc_export_exchange.restype = ctypes.c_int
+        L.p3d_mc_export_exchange.argtypes = [dp, vp, vp, vp]
+        L.p3d_mc_faces_exchanged.restype = ctypes.c_int
+        L.p3d_mc_faces_exchanged.argtypes = [dp, vp, vp, ctypes.c_int, ctypes.c_int, vp, i64, vp]
         L.p3d_mc_faces.restype = ctypes.c_int
         L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
@@ -119,11 +127,40 @@ def _grid_ok(grid):
     return GRID_DTYPES[grid.dtype]
 
 
+_sizes = {}   # descriptor bytes -> (workspace bytes, vertex capacity hint): both depend on the shape fields only
+
+
+def _desc_sizes(desc):
+    key = bytes(desc)
+    hit = _sizes.get(key)
+    if hit is None:
+        n = lib().p3d_mc_workspace_bytes(ctypes.byref(desc))
+        if n == 0:
+            raise P3DError(P3D_ERR_INVALID, "invalid descriptor")
+        if len(_sizes) > 256:
+            _sizes.clear()
+        hit = _sizes[key] = (n, lib().p3d_mc_vertex_capacity_hint(ctypes.byref(desc)))
+    return hit
+
+
 def mc_workspace_bytes(desc):
-    n = lib().p3d_mc_workspace_bytes(ctypes.byref(desc))
-    if n == 0:
-        raise P3DError(P3D_ERR_INVALID, "invalid descriptor")
-    return n
+    return _desc_sizes(desc)[0]
+
+
+class _on_device:
+    """torch.cuda.device(...) only when the tensor's device is not already current (the context manager costs
+    several microseconds per extraction)."""
+
+    def __init__(self, device):
+        self.ctx = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def mc_count(desc, grid, workspace=None, vertex_capacity=None):
@@ -172,15 +209,16 @@ def mc_extract(desc, grid, vertex_capacity=None, face_capacity=None):
     buffers of speculative capacity (None = the library's vertex hint, twice that many faces); whatever did not
     fit is redone into an exact buffer.  -> (vertices f32 [V,3], faces i32 [F,3], V, F)."""
     dtype = _grid_ok(grid)
-    ws = torch.empty(mc_workspace_bytes(desc), dtype=torch.uint8, device=grid.device)
+    ws_bytes, hint = _desc_sizes(desc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grid.device)
     if vertex_capacity is None:
-        vertex_capacity = lib().p3d_mc_vertex_capacity_hint(ctypes.byref(desc))
+        vertex_capacity = hint
     if face_capacity is None:
         face_capacity = 2 * int(vertex_capacity)
     vbuf = torch.empty((int(vertex_capacity), 3), dtype=torch.float32, device=grid.device)
     fbuf = torch.empty((int(face_capacity), 3), dtype=torch.int32, device=grid.device)
     counts = (ctypes.c_int64 * 2)()
-    with torch.cuda.device(grid.device):
+    with _on_device(grid.device):
         check(lib().p3d_mc_extract(ctypes.byref(desc), grid.data_ptr(), dtype, ws.data_ptr(), ws.numel(),
                                    vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity),
                                    fbuf.data_ptr() if face_capacity else None, int(face_capacity), counts, _stream()))

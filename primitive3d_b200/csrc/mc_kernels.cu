@@ -673,7 +673,9 @@ __device__ __forceinline__ uint32_t corner_code(const uint4 &w, const uint4 &n, 
 }
 
 __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
-    k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces, unsigned long long face_capacity) {
+    k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces, unsigned long long face_capacity,
+            int vertex_base_from_header) {
+    if (vertex_base_from_header) vbase += (int32_t)ws.header->vertex_base;  // multi-GPU: computed by k_apply_exchange
     // speculative launch (p3d_mc_extract): the buffer was sized before F was known; if it is too small nothing is
     // written and the caller runs the pass again with an exact buffer
     if (ws.header->total_f > face_capacity) return;
@@ -1085,7 +1087,7 @@ __global__ void __launch_bounds__(kRoundTiles) k_round_sums(McGeom g, McWorkspac
 }
 
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
-                  cudaStream_t s) {
+                  bool vertex_base_from_header, cudaStream_t s) {
     if (g.npieces <= 0) return;
     k_round_sums<<<(unsigned)g.nfrounds, kRoundTiles, 0, s>>>(g, ws);
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
@@ -1097,7 +1099,8 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     (void)attr;
     cudaMemsetAsync(&ws.header->ticket_faces, 0, sizeof(unsigned int), s);
     k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces,
-                                                                                         (unsigned long long)face_capacity);
+                                                                                         (unsigned long long)face_capacity,
+                                                                                         vertex_base_from_header ? 1 : 0);
 }
 
 // Multi-GPU.  Export: the first plane's table entries (shard-local ids).  Import: install the next shard's
@@ -1108,6 +1111,50 @@ __global__ void k_shift_plane(uint4 *__restrict__ dst, const uint4 *__restrict__
         const uint4 t = src[i];
         dst[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, 0u);
     }
+}
+
+// Device-side exchange (no host round trip between the two passes).  Export: first-plane table entries followed by
+// {V, F}.  Apply: vertex_base = sum of the lower shards' V; the next shard's first-plane entries, shifted by this
+// shard's V, become this shard's halo-plane numbering.
+__global__ void k_export_exchange(uint4 *__restrict__ dst, const uint4 *__restrict__ src, int64_t n, const McHeader *header) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint4 t = src[i];
+        dst[i] = make_uint4(t.x, t.y, t.z, 0u);
+    } else if (i == n) {
+        const unsigned long long v = header->total_v, f = header->total_f;
+        dst[n] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)f, (uint32_t)(f >> 32));
+    }
+}
+
+__global__ void k_apply_exchange(McWorkspace ws, uint4 *__restrict__ halo, const uint4 *__restrict__ gathered, int64_t n,
+                                 int rank, int world) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        unsigned long long base = 0;
+        for (int r = 0; r < rank; ++r) {
+            const uint4 c = gathered[(int64_t)r * (n + 1) + n];
+            base += (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+        }
+        ws.header->vertex_base = base;
+    }
+    if (i < n && rank + 1 < world) {
+        const uint32_t delta = (uint32_t)ws.header->total_v;
+        const uint4 t = gathered[(int64_t)(rank + 1) * (n + 1) + i];
+        halo[i] = make_uint4(t.x + delta, t.y + delta, t.z + delta, 0u);
+    }
+}
+
+void launch_export_exchange(uint32_t *out, const McGeom &g, const McWorkspace &ws, cudaStream_t s) {
+    const int64_t n = g.ry * (int64_t)g.np;
+    k_export_exchange<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint4 *>(out), ws.ptab, n, ws.header);
+}
+
+void launch_apply_exchange(const McGeom &g, const McWorkspace &ws, const uint32_t *gathered, int rank, int world,
+                           cudaStream_t s) {
+    const int64_t n = g.ry * (int64_t)g.np;
+    k_apply_exchange<<<(unsigned)((n + 255) / 256 > 0 ? (n + 255) / 256 : 1), 256, 0, s>>>(
+        ws, ws.ptab + g.owned_x * n, reinterpret_cast<const uint4 *>(gathered), n, rank, world);
 }
 
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s) {

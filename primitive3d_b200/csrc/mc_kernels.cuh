@@ -64,6 +64,7 @@ struct McHeader {
     unsigned int ticket;         // dynamic tile id of k_tile
     unsigned int ticket_faces;   // dynamic chunk id of k_faces (reset by launch_faces)
     unsigned int pad[2];
+    unsigned long long vertex_base;  // sum of the lower shards' V, computed on the device from the exchange buffer
 };
 
 // State of one single-pass scan (two levels: items, rounds of 256 items).  Zeroed before use.
@@ -98,8 +99,14 @@ struct McEmitParams {
 void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
                       float *verts, int64_t vertex_capacity, int mode, cudaStream_t s);
 // face_capacity: faces the buffer holds; the pass writes nothing if the workspace's F exceeds it
+// vertex_base_from_header: add header->vertex_base (launch_apply_exchange) to every face index
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
-                  cudaStream_t s);
+                  bool vertex_base_from_header, cudaStream_t s);
+// Multi-GPU exchange without the host: `out` = this shard's first-plane table + {V, F} (two int64) appended;
+// `gathered` = the all-gather of every shard's `out` ([world][words + 4] int32).
+void launch_export_exchange(uint32_t *out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
+void launch_apply_exchange(const McGeom &g, const McWorkspace &ws, const uint32_t *gathered, int rank, int world,
+                           cudaStream_t s);
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor

@@ -213,7 +213,7 @@ p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t 
     const Layout l = make_layout(g);
     const p3d::McWorkspace ws = bind(const_cast<void *>(workspace), l);
     p3d::McEmitParams prm = make_params(desc, vertex_id_base);
-    p3d::launch_faces(g, ws, prm, faces, INT64_MAX, static_cast<cudaStream_t>(stream));
+    p3d::launch_faces(g, ws, prm, faces, INT64_MAX, false, static_cast<cudaStream_t>(stream));
     P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }
@@ -239,7 +239,7 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
     P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
     p3d::launch_tile_pass(grid, dtype, g, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
     if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_extract: ") + p3d::tile_pass_error());
-    if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, s);
+    if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, false, s);
     P3D_CUDA(cudaGetLastError());
     int64_t *pin = pinned_counts();
     int64_t *dst = pin ? pin : counts_host;
@@ -249,6 +249,55 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
     counts_host[1] = dst[1];
     if (counts_host[0] > INT32_MAX)
         return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract: vertex count exceeds the int32 face-index contract");
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_tile_async(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, size_t workspace_bytes,
+                             float *vertices, int64_t vertex_capacity, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: invalid descriptor");
+    if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: unknown dtype");
+    if (!grid || !workspace) return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: null pointer");
+    if (desc->global_rx < 1) return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: global_rx must be >= 1");
+    if (vertex_capacity < 0 || (vertex_capacity > 0 && !vertices))
+        return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: vertex_capacity without a vertex buffer");
+    const Layout l = make_layout(g);
+    if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_tile_async: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_tile_async: workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
+    p3d::launch_tile_pass(grid, dtype, g, bind(workspace, l), make_params(desc, 0), vertices, vertex_capacity, 0, s);
+    if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_tile_async: ") + p3d::tile_pass_error());
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+int64_t p3d_mc_exchange_words(const p3d_mc_desc *desc) {
+    const int64_t w = p3d_mc_plane_table_words(desc);
+    return w ? w + 4 : 0;
+}
+
+p3d_status p3d_mc_export_exchange(const p3d_mc_desc *desc, const void *workspace, uint32_t *out, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !workspace || !out) return fail(P3D_ERR_INVALID, "p3d_mc_export_exchange: invalid argument");
+    p3d::launch_export_exchange(out, g, bind(const_cast<void *>(workspace), make_layout(g)), static_cast<cudaStream_t>(stream));
+    P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_faces_exchanged(const p3d_mc_desc *desc, void *workspace, const uint32_t *gathered, int rank, int world,
+                                  int32_t *faces, int64_t face_capacity, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !workspace || !gathered) return fail(P3D_ERR_INVALID, "p3d_mc_faces_exchanged: invalid argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(P3D_ERR_INVALID, "p3d_mc_faces_exchanged: bad rank / world");
+    if ((rank + 1 < world) != (g.rx == g.owned_x + 1))
+        return fail(P3D_ERR_INVALID, "p3d_mc_faces_exchanged: every shard but the last must carry a halo plane");
+    if (face_capacity < 0 || (face_capacity > 0 && !faces)) return fail(P3D_ERR_INVALID, "p3d_mc_faces_exchanged: capacity without a buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const p3d::McWorkspace ws = bind(workspace, make_layout(g));
+    p3d::launch_apply_exchange(g, ws, gathered, rank, world, s);
+    if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, true, s);
+    P3D_CUDA(cudaGetLastError());
     return P3D_OK;
 }
 

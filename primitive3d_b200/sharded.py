@@ -69,6 +69,13 @@ def exchange_counts_and_tables(V, F, table, group=None):
     return [tuple(c) for c in counts], out[:, :words]
 
 
+def unpack_counts(gathered, world, words):
+    """(V_r, F_r) of every rank from the gathered exchange payloads (int32 [world * words], the last four words
+    of each payload are the two int64 counts).  The device-to-host copy is the extraction's only synchronisation."""
+    tail = gathered.view(world, words)[:, words - 4:].contiguous().view(torch.int64).cpu().tolist()
+    return [tuple(c) for c in tail]
+
+
 _last_vertex_count = {}   # slab shape -> V of its last extraction (sizes the speculative vertex buffer)
 _last_face_count = {}     # slab shape -> F of its last extraction (single GPU: sizes the speculative face buffer)
 
@@ -120,25 +127,40 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
             _last_face_count.clear()
         _last_vertex_count[key], _last_face_count[key] = V, F
         return SlabMesh(verts, faces, 0, 0, V, F)
-    V, F, ws, vbuf = capi.mc_count(desc, slab, vertex_capacity=vertex_capacity)
-    if len(_last_vertex_count) > 64:
-        _last_vertex_count.clear()
-    _last_vertex_count[tuple(int(s) for s in slab.shape)] = V
-    verts = capi.mc_vertices(desc, slab, ws, V, vbuf)   # local: needs nothing from the other ranks
-
+    # Several GPUs: tile pass, exchange and face pass are all queued; the host waits once, for the gathered counts.
+    # The exchange payload (first-plane numbering table + {V, F}) is written, gathered and consumed on the device:
+    # the vertex id base and the halo-plane numbering never pass through the host.
     L = capi.lib()
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    # numbering of the boundary plane: everybody publishes the piece table of its first plane, and its counts
-    # ride along in the same all-gather
-    words = L.p3d_mc_plane_table_words(ctypes.byref(desc))
-    table = torch.empty(words, dtype=torch.int32, device=slab.device)
-    capi.check(L.p3d_mc_export_first_plane(ctypes.byref(desc), ws.data_ptr(), table.data_ptr(), stream))
-    counts, tables = exchange_counts_and_tables(V, F, table, group)
+    dtype = capi._grid_ok(slab)
+    dev = slab.device
+    ws_bytes, hint = capi._desc_sizes(desc)
+    if vertex_capacity is None:
+        vertex_capacity = hint
+    f_prev = _last_face_count.get(key)
+    face_capacity = 2 * int(vertex_capacity) if f_prev is None else f_prev + f_prev // 16 + 4096
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    vbuf = torch.empty((int(vertex_capacity), 3), dtype=torch.float32, device=dev)
+    fbuf = torch.empty((int(face_capacity), 3), dtype=torch.int32, device=dev)
+    words = L.p3d_mc_exchange_words(ctypes.byref(desc))
+    mine = torch.empty(words, dtype=torch.int32, device=dev)
+    gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
+    with capi._on_device(dev):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        capi.check(L.p3d_mc_tile_async(ctypes.byref(desc), slab.data_ptr(), dtype, ws.data_ptr(), ws.numel(),
+                                       vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity), stream))
+        capi.check(L.p3d_mc_export_exchange(ctypes.byref(desc), ws.data_ptr(), mine.data_ptr(), stream))
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        capi.check(L.p3d_mc_faces_exchanged(ctypes.byref(desc), ws.data_ptr(), gathered.data_ptr(), rank, world,
+                                            fbuf.data_ptr() if face_capacity else None, int(face_capacity), stream))
+    counts = unpack_counts(gathered, world, words)          # the only synchronisation
+    V, F = counts[rank]
     v_off, f_off, v_tot, f_tot = exclusive_offsets(counts, rank)
     if v_tot > 2 ** 31 - 1:
         raise OverflowError("global vertex count exceeds the int32 face-index contract")
-    if rank + 1 < world:
-        nxt = tables[rank + 1].contiguous()
-        capi.check(L.p3d_mc_import_halo_plane(ctypes.byref(desc), ws.data_ptr(), nxt.data_ptr(), int(V), stream))
-    faces = capi.mc_faces(desc, ws, F, v_off)
+    if len(_last_vertex_count) > 64:
+        _last_vertex_count.clear()
+        _last_face_count.clear()
+    _last_vertex_count[key], _last_face_count[key] = V, F
+    verts = capi.mc_vertices(desc, slab, ws, V, vbuf)       # exact-size second pass only if the guess was too small
+    faces = fbuf[:F] if F <= face_capacity else capi.mc_faces(desc, ws, F, v_off)   # halo numbering is installed
     return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)

@@ -101,3 +101,55 @@ def test_virtual_shards_reproduce_single_gpu_result(shape, world, seed):
     from canonical import assert_same_mesh
     assert_same_mesh(torch.cat(vs).cpu().numpy(), torch.cat(fs).cpu().numpy(), ref_v.cpu().numpy(), ref_f.cpu().numpy(),
                      ordered_faces=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,world,seed", [((12, 20, 40), 2, 4), ((13, 9, 270), 3, 5), ((64, 64, 64), 8, 6)])
+def test_virtual_shards_device_side_exchange(shape, world, seed):
+    """The multi-GPU fast path (p3d_mc_tile_async -> p3d_mc_export_exchange -> all-gather -> p3d_mc_faces_exchanged)
+    with the all-gather played by a concatenation on one GPU: vertex id bases and halo numbering are computed on the
+    device; the concatenated shards must equal the single-GPU arrays, whatever the face capacity guess."""
+    from primitive3d_b200 import capi
+    from primitive3d_b200.sharded import slab_range, slab_with_halo, unpack_counts
+    L = capi.lib()
+    grid = torch.from_numpy(inputs.noise(shape, seed)).cuda()
+    n = shape[0]
+    ref_v, ref_f = capi.marching_cubes(grid, -0.05)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shards, payloads = [], []
+    for r in range(world):
+        x0, x1 = slab_range(n, world, r)
+        slab = grid[x0:slab_with_halo(n, world, r)[1]].contiguous()
+        desc = capi.McDesc.make(slab.shape, -0.05, owned_x=x1 - x0, x_origin=x0, global_rx=n,
+                                upper=[float(s) for s in shape])
+        ws = torch.empty(capi.mc_workspace_bytes(desc), dtype=torch.uint8, device="cuda")
+        vbuf = torch.empty((slab.numel() * 3, 3), dtype=torch.float32, device="cuda")
+        capi.check(L.p3d_mc_tile_async(ctypes.byref(desc), slab.data_ptr(), 0, ws.data_ptr(), ws.numel(), vbuf.data_ptr(),
+                                       vbuf.shape[0], stream))
+        words = L.p3d_mc_exchange_words(ctypes.byref(desc))
+        mine = torch.empty(words, dtype=torch.int32, device="cuda")
+        capi.check(L.p3d_mc_export_exchange(ctypes.byref(desc), ws.data_ptr(), mine.data_ptr(), stream))
+        shards.append(dict(desc=desc, ws=ws, vbuf=vbuf, slab=slab))
+        payloads.append(mine)
+    gathered = torch.cat(payloads)
+    counts = unpack_counts(gathered, world, words)
+    assert sum(c[0] for c in counts) == ref_v.shape[0] and sum(c[1] for c in counts) == ref_f.shape[0]
+    vs, fs = [], []
+    for r, s in enumerate(shards):
+        V, F = counts[r]
+        for fcap in (F, F + 3):
+            fbuf = torch.full((fcap, 3), -7, dtype=torch.int32, device="cuda")
+            capi.check(L.p3d_mc_faces_exchanged(ctypes.byref(s["desc"]), s["ws"].data_ptr(), gathered.data_ptr(), r, world,
+                                                fbuf.data_ptr(), fcap, stream))
+        if F:   # too small a guess: nothing is written
+            small = torch.full((F - 1 if F > 1 else 1, 3), -7, dtype=torch.int32, device="cuda")
+            capi.check(L.p3d_mc_faces_exchanged(ctypes.byref(s["desc"]), s["ws"].data_ptr(), gathered.data_ptr(), r, world,
+                                                small.data_ptr(), F - 1, stream))
+            assert bool((small == -7).all())
+        vs.append(s["vbuf"][:V])
+        fs.append(fbuf[:F])
+        assert bool((fbuf[F:] == -7).all())
+    torch.cuda.synchronize()
+    from canonical import assert_same_mesh
+    assert_same_mesh(torch.cat(vs).cpu().numpy(), torch.cat(fs).cpu().numpy(), ref_v.cpu().numpy(), ref_f.cpu().numpy(),
+                     ordered_faces=True)
