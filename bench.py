@@ -15,8 +15,10 @@ that is already resident in HBM.
 metric = Gvoxel/s = Rx*Ry*Rz / t, t from CUDA events on the launching stream, max over ranks.
 The line also carries the per-kernel roofline numbers (kernels timed one by one with CUDA events
 in a separate loop of the same run), the whole-path achieved GB/s, a CPU baseline timed on this
-box's host cores on a bounded sample, the end-to-end number through prim3d.marching_cubes with
-host buffers, and the SM clocks sampled while the GPU was busy.
+box's host cores on a bounded sample, the end-to-end number with HOST buffers (N = 1: the C-ABI call
+p3d_mc_extract_host, pinned grid in, pinned mesh out, slabs pipelined so that upload, extraction and
+download overlap; the reference's call shape, prim3d.marching_cubes + the caller's copy back, is
+timed beside it), and the SM clocks sampled while the GPU was busy.
 
 --impl reference times the reference's CPU path for the same workload: there is no GPU in that
 arm; it runs the OpenMP port of the reference algorithm (oracle/mc_oracle.c) on all host threads
@@ -249,34 +251,51 @@ def main():
         hv = torch.empty((out.vertices.shape[0], 3), dtype=torch.float32).pin_memory()
         hf = torch.empty((out.faces.shape[0], 3), dtype=torch.int32).pin_memory()
         del out
-        e2e_t = []
-        for i in range(2 + 3):
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t = time.perf_counter()
-            if world == 1:
-                v, f = prim3d.marching_cubes(host, 0.0)      # H2D inside the wrapper (.cuda())
-            else:
-                o = sharded.marching_cubes_slab(host.to(dev, non_blocking=True), 0.0, x0, n)
-                v, f = o.vertices, o.faces
+        def timed_e2e(call):
+            ts = []
+            for i in range(2 + 3):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t = time.perf_counter()
+                call()
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                if i >= 2:
+                    ts.append(float(dt.item()))
+            return statistics.mean(ts)
+
+        def via_reference_api():       # the reference's call shape: .cuda() inside the wrapper, caller copies back
+            v, f = prim3d.marching_cubes(host, 0.0)
             hv.copy_(v, non_blocking=True)
             hf.copy_(f, non_blocking=True)
-            torch.cuda.synchronize()
-            dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            if i >= 2:
-                e2e_t.append(float(dt.item()))
-            del v, f
-        sec = statistics.mean(e2e_t)
+
+        def via_sharded_driver():
+            o = sharded.marching_cubes_slab(host.to(dev, non_blocking=True), 0.0, x0, n)
+            hv.copy_(o.vertices, non_blocking=True)
+            hf.copy_(o.faces, non_blocking=True)
+
+        def via_host_abi():            # C ABI with host buffers: slabs pipelined, upload / extraction / download overlap
+            capi.marching_cubes_host(host, 0.0, vertices_out=hv, faces_out=hf)
+
         io = torch.tensor([host.numel() * 4, hv.numel() * 4 + hf.numel() * 4], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(io)
+        if world == 1:
+            sec = timed_e2e(via_host_abi)
+            sec_ref_api = timed_e2e(via_reference_api)
+            api = "p3d_mc_extract_host (C ABI, pinned host grid in, pinned host mesh out, slab-pipelined)"
+        else:
+            sec, sec_ref_api = timed_e2e(via_sharded_driver), None
+            api = "primitive3d_b200.sharded.marching_cubes_slab(pinned host slab -> device) + D2H of the shard"
         e2e = {"value": n ** 3 / sec / 1e9, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(io[0]),
-               "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3,
-               "api": "prim3d.marching_cubes(pinned host tensor) + D2H of vertices and faces" if world == 1 else
-                      "primitive3d_b200.sharded.marching_cubes_slab(pinned host slab -> device) + D2H of the shard"}
+               "d2h_bytes_per_step": int(io[1]), "ms_per_step": sec * 1e3, "api": api}
+        if sec_ref_api is not None:
+            e2e["via_prim3d_marching_cubes"] = {"value": n ** 3 / sec_ref_api / 1e9, "ms_per_step": sec_ref_api * 1e3,
+                                                "api": "prim3d.marching_cubes(pinned host tensor) + D2H of vertices and "
+                                                       "faces: upload, extraction and download one after the other"}
         del host, hv, hf
 
     if rank != 0:

@@ -181,6 +181,28 @@ p3d_status p3d_mc_export_exchange(const p3d_mc_desc *desc, const void *workspace
 p3d_status p3d_mc_faces_exchanged(const p3d_mc_desc *desc, void *workspace, const uint32_t *gathered, int rank,
                                   int world, int32_t *faces, int64_t face_capacity, void *stream);
 
+/* Marching cubes of a grid in HOST memory, pipelined slab by slab on one device: while slab k is
+ * extracted, slab k+1 uploads and the mesh of slab k-1 downloads, so the call costs about
+ * max(upload, download) instead of upload + compute + download (the reference wrapper's
+ * `.cuda()` ... caller's `.cpu()`, prim3d/utility/marching_cubes.py:86-95), and the device holds
+ * two slabs at a time -- the grid may be larger than device memory.
+ *   desc          the whole grid (owned_x = rx = global_rx, x_origin = 0);
+ *   host_grid     rx*ry*rz elements of `dtype` in host memory (pinned memory for full PCIe speed);
+ *   slab_planes   dim-0 planes per slab (rounded up to a multiple of 8), 0 = choose (~16 slabs);
+ *   host_vertices float[3*vertex_capacity], host_faces int32[3*face_capacity] (host memory);
+ *   counts_host   {V, F}.  The outputs are complete iff V <= vertex_capacity and F <= face_capacity
+ *                 (otherwise call again with buffers of the returned sizes);
+ *   device_arena  optional device scratch of p3d_mc_extract_host_arena_bytes() bytes, 256-byte
+ *                 aligned (two slabs + their workspaces and output buffers), e.g. from the caller's
+ *                 caching allocator; NULL or too small: cudaMalloc / cudaFree inside the call.
+ * Vertices are numbered slab by slab (the multi-GPU numbering with world = number of slabs), faces
+ * are in voxel-major order with global ids.  Uses its own streams; synchronous for the caller. */
+size_t p3d_mc_extract_host_arena_bytes(const p3d_mc_desc *desc, int dtype, int64_t slab_planes);
+p3d_status p3d_mc_extract_host(const p3d_mc_desc *desc, const void *host_grid, int dtype, int64_t slab_planes,
+                               float *host_vertices, int64_t vertex_capacity, int32_t *host_faces,
+                               int64_t face_capacity, int64_t *counts_host, void *device_arena,
+                               size_t arena_bytes);
+
 /* One-shot convenience for C/C++ callers: workspace and a vertex buffer of
  * p3d_mc_vertex_capacity_hint() through the callback, count, faces (and an exact vertex buffer
  * + p3d_mc_vertices if the hint was too small).  alloc(ctx, bytes) must return device memory on

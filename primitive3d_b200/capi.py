@@ -74,6 +74,10 @@ def lib():
         L.p3d_mc_export_exchange.argtypes = [dp, vp, vp, vp]
         L.p3d_mc_faces_exchanged.restype = ctypes.c_int
         L.p3d_mc_faces_exchanged.argtypes = [dp, vp, vp, ctypes.c_int, ctypes.c_int, vp, i64, vp]
+        L.p3d_mc_extract_host.restype = ctypes.c_int
+        L.p3d_mc_extract_host.argtypes = [dp, vp, ctypes.c_int, i64, vp, i64, vp, i64, ctypes.POINTER(i64), vp, sz]
+        L.p3d_mc_extract_host_arena_bytes.restype = sz
+        L.p3d_mc_extract_host_arena_bytes.argtypes = [dp, ctypes.c_int, i64]
         L.p3d_mc_faces.restype = ctypes.c_int
         L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
@@ -226,6 +230,50 @@ def mc_extract(desc, grid, vertex_capacity=None, face_capacity=None):
     verts = mc_vertices(desc, grid, ws, V, vbuf)
     faces = fbuf[:F] if F <= face_capacity else mc_faces(desc, ws, F)
     return verts, faces, V, F
+
+
+def marching_cubes_host(grid, thresh, lower=None, upper=None, slab_planes=0, vertices_out=None, faces_out=None,
+                        device=None):
+    """Marching cubes of a grid in HOST memory, slab-pipelined on one GPU (p3d_mc_extract_host): upload, extraction
+    and download overlap, and the grid may be larger than device memory.
+
+    grid: contiguous CPU tensor [Rx,Ry,Rz] of a supported dtype (pin it for full PCIe speed).  vertices_out /
+    faces_out: optional CPU tensors (float32 [cap,3] / int32 [cap,3], ideally pinned) to write into; otherwise
+    pinned buffers are allocated from the library's hint.  Returns (vertices float32 [V,3], faces int32 [F,3]) as
+    CPU tensors (views of the buffers); a too small buffer is replaced by one of the exact size and the call
+    repeated.  Vertex numbering is slab by slab, faces are voxel-major with global ids."""
+    if grid.is_cuda or not grid.is_contiguous() or grid.dtype not in GRID_DTYPES or grid.dim() != 3:
+        raise ValueError("grid must be a contiguous CPU tensor [Rx,Ry,Rz] of a supported dtype")
+    if not torch.cuda.is_available():
+        raise RuntimeError("marching_cubes_host needs a CUDA device (there is no CPU fallback)")
+    desc = McDesc.make(grid.shape, thresh, lower, upper)
+    hint = _desc_sizes(desc)[1]
+    pin = lambda n, dt: torch.empty((int(n), 3), dtype=dt).pin_memory()
+    if vertices_out is None:
+        vertices_out = pin(hint, torch.float32)
+    if faces_out is None:
+        faces_out = pin(2 * hint, torch.int32)
+    for _ in range(2):
+        for t, dt in ((vertices_out, torch.float32), (faces_out, torch.int32)):
+            if t.is_cuda or not t.is_contiguous() or t.dtype != dt or t.dim() != 2 or t.shape[1] != 3:
+                raise ValueError("output buffers must be contiguous CPU tensors [cap,3] (float32 vertices, int32 faces)")
+        counts = (ctypes.c_int64 * 2)()
+        with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+            # device scratch from torch's caching allocator: cudaMalloc / cudaFree would cost more than a slab
+            nbytes = lib().p3d_mc_extract_host_arena_bytes(ctypes.byref(desc), GRID_DTYPES[grid.dtype], int(slab_planes))
+            arena = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            check(lib().p3d_mc_extract_host(ctypes.byref(desc), grid.data_ptr(), GRID_DTYPES[grid.dtype], int(slab_planes),
+                                            vertices_out.data_ptr(), vertices_out.shape[0], faces_out.data_ptr(),
+                                            faces_out.shape[0], counts, arena.data_ptr(), arena.numel()))
+            del arena   # the call is synchronous: nothing is in flight
+        V, F = counts[0], counts[1]
+        if V <= vertices_out.shape[0] and F <= faces_out.shape[0]:
+            return vertices_out[:V], faces_out[:F]
+        if V > vertices_out.shape[0]:
+            vertices_out = pin(V, torch.float32)
+        if F > faces_out.shape[0]:
+            faces_out = pin(F, torch.int32)
+    raise P3DError(P3D_ERR_INVALID, "marching_cubes_host: counts changed between two passes over the same grid")
 
 
 def marching_cubes(grid, thresh, lower=None, upper=None, vertex_capacity=None):

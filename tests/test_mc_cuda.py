@@ -209,6 +209,27 @@ def test_ply_assembled_on_the_device_has_the_same_bytes(tmp_path, nv, nf):
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+@pytest.mark.parametrize("shape,planes,dtype", [((40, 24, 140), 8, np.float32), ((37, 20, 64), 16, np.float32),
+                                                 ((16, 16, 16), 0, np.float32), ((50, 12, 33), 8, np.float64),
+                                                 ((9, 8, 8), 8, np.int64)])
+def test_host_streamed_extraction_equals_single_shot(shape, planes, dtype):
+    """p3d_mc_extract_host (grid and mesh in host memory, slabs pipelined through the device) gives the mesh of the
+    single-shot call: same faces in the same voxel-major order over a vertex array numbered slab by slab."""
+    from primitive3d_b200 import capi
+    g = inputs.noise(shape, sum(shape))
+    g = (g * 1000).astype(dtype) if dtype == np.int64 else g.astype(dtype)
+    host = torch.from_numpy(np.ascontiguousarray(g)).pin_memory()
+    lower, upper = [-1.0, 0.5, 2.0], [3.0, 4.5, 2.5]
+    v0, f0 = capi.marching_cubes(host.cuda(), 0.05, lower, upper)
+    v, f = capi.marching_cubes_host(host, 0.05, lower, upper, slab_planes=planes)
+    assert not v.is_cuda and v.dtype == torch.float32 and f.dtype == torch.int32
+    assert_same_mesh(v.numpy(), f.numpy(), v0.cpu().numpy(), f0.cpu().numpy(), ordered_faces=True)
+    # too small output buffers: the counts come back and the call is repeated with exact ones
+    v2, f2 = capi.marching_cubes_host(host, 0.05, lower, upper, slab_planes=planes,
+                                      vertices_out=torch.empty((5, 3)), faces_out=torch.empty((7, 3), dtype=torch.int32))
+    assert torch.equal(v2, v) and torch.equal(f2, f)
+
+
 def test_unsupported_dtype_is_cast_by_the_wrapper():
     import prim3d
     g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
