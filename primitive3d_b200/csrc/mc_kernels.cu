@@ -168,8 +168,8 @@ __device__ __forceinline__ bool scan_prefix(const McScan &sc, uint32_t item, int
 // vertex id -> write vertices (position = integer corner + dt on one axis) and the table entries.  The
 // load of the next tile and the wait for the scan overlap.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRing = 1728;     // pending crossing edges of a CTA (6 bytes each): ~5 tiles of the gyroid case
-constexpr int kQueue = 8;       // pending tiles of a CTA
+constexpr int kRing = 1408;     // pending crossing edges of a CTA (6 bytes each): ~4.5 tiles of the gyroid case
+constexpr int kQueue = 4;       // pending tiles of a CTA
 constexpr int kSbitsStride = 8;
 constexpr int kRowPitch = kTileY + 1;  // staged rows per plane
 
@@ -188,6 +188,7 @@ struct TileSmem {
     int8_t ntri[256];      // indexed by the corner bits in staging order a0 a1 b0 b1 c0 c1 d0 d1:
                            // the case's correction  #triangles - (#crossed edges - 2)
     PendingTile q[kQueue];
+    uint2 prel[kQueue][kTileX * kTileY];  // table entries of the pending tiles, relative to the tile: {vx | vy << 16, vz | nf << 16}
     unsigned long long bar;
     unsigned long long base;       // result of warp 0's non-blocking look-back at the top of an iteration
     unsigned long long base_wait;  // result of a blocking look-back
@@ -297,36 +298,30 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     // Queue state, identical in every thread:
     uint32_t q_head = 0, q_count = 0, ring_used = 0, ring_tail = 0;
 
-    // the table entries of a tile were written relative to the tile (count phase, by thread 4 * row): once its first
-    // vertex id is known the same thread makes them absolute, so the face pass needs no per-tile indirection
-    // (load issued before the tile's vertices are written, add + store after: the round trip to L2 is hidden)
-    auto table_entry = [&](const int4 &c) -> uint4 * {
-        if (mode != 0 || (tid & 3) != 0) return nullptr;
-        const int tx = c.x + (tid >> 5), ty = c.y + ((tid >> 2) & 7);
-        return (tx < ox && ty < ry) ? ws.ptab + ((int64_t)tx * ry + ty) * np + c.z : nullptr;
-    };
-    auto load_entry = [&](const uint4 *e) {
-        uint4 t = make_uint4(0, 0, 0, 0);
-        if (e) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(e) : "memory");
-        return t;
-    };
-    auto finish_entry = [&](uint4 *e, uint4 t, const int4 &c, unsigned long long base, uint32_t count) {
-        if (e) *e = make_uint4(t.x + (uint32_t)base, t.y + (uint32_t)base, t.z + (uint32_t)base, t.w);
+    // The table entries of a tile {first x-/y-/z-edge vertex id, triangle count} per (row, piece) are known relative
+    // to the tile in the count phase; they wait in shared memory with the tile's vertices and are written once,
+    // absolute, when the tile's first vertex id is known: the face pass needs no per-tile indirection and the
+    // table is never read back.  Thread 4 * row writes the entry of its row.
+    auto write_entry = [&](const int4 &c, uint2 rel, unsigned long long base, uint32_t count) {
+        if (mode == 0 && (tid & 3) == 0) {
+            const int tx = c.x + (tid >> 5), ty = c.y + ((tid >> 2) & 7);
+            if (tx < ox && ty < ry)
+                ws.ptab[((int64_t)tx * ry + ty) * np + c.z] =
+                    make_uint4((rel.x & 0xffffu) + (uint32_t)base, (rel.x >> 16) + (uint32_t)base, (rel.y & 0xffffu) + (uint32_t)base, rel.y >> 16);
+        }
         if (mode == 0 && tid == 0 && (uint32_t)c.w == ntiles - 1) ws.header->total_v = base + count;
     };
     // vertices of the pending tile in queue slot `slot`, whose first vertex id is `base`
     auto retire = [&](uint32_t slot, unsigned long long base) {
         const int4 c = S.q[slot].coord;
         const uint32_t start = S.q[slot].start, count = S.q[slot].count;
-        uint4 *const te = table_entry(c);
-        const uint4 tv = load_entry(te);
+        write_entry(c, S.prel[slot][tid >> 2], base, count);
         for (uint32_t k = tid; k < count; k += kTileThreads) {
             uint32_t idx = start + k;
             if (idx >= (uint32_t)kRing) idx -= kRing;
             const unsigned long long id = base + k;
             if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
         }
-        finish_entry(te, tv, c, base, count);
         ring_used -= count;
         q_head = (q_head + 1) % kQueue;
         --q_count;
@@ -524,8 +519,8 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             scan_publish(ws.vscan, tile, vt, ntiles);
         }
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
-        // table entry of my (row, piece): first ids relative to the tile; made absolute by finish_table()
-        if (mode == 0 && own && w == 0) ws.ptab[grow * np + p] = make_uint4(vx_rel, vy_rel, vz_rel, nf);
+        // table entry of my (row, piece), relative to the tile (every field < 2^16: a tile has <= 24576 vertices)
+        const uint2 my_entry = make_uint2(vx_rel | (vy_rel << 16), vz_rel | (nf << 16));
         const uint32_t first[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
         const uint32_t wmask[3] = {m0, m1, m2};
         const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
@@ -540,6 +535,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             }
             // ---- my crossing edges -> ring; my warp interpolates its own (contiguous) range ----
             const uint32_t start = ring_tail;
+            if (w == 0) S.prel[(q_head + q_count) % kQueue][r] = my_entry;
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
                 uint32_t pos = start + first[ax];
@@ -576,10 +572,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 retire(q_head, tb);
             }
             const unsigned long long tb = wait_base(tile);
-            {
-                uint4 *const te = table_entry(tc);
-                finish_entry(te, load_entry(te), tc, tb, vt);
-            }
+            write_entry(tc, my_entry, tb, vt);  // thread 4 * row holds the entry of its row
             for (uint32_t c0 = 0; c0 < vt; c0 += kRing) {
 #pragma unroll
                 for (int ax = 0; ax < 3; ++ax) {
