@@ -377,6 +377,34 @@ def main():
             except Exception as exc:  # the comparison is informative only
                 line["reference_cuda_gyroid512"] = {"error": str(exc)[:200]}
 
+        # ---- marching tetrahedra, BASELINE configs[3] (Kuhn tet grid 128^3), beside the reference's torch ops on this GPU ----
+        try:
+            from oracle import inputs as oin   # input generator only
+            pts, tets, sdf = oin.kuhn_tet_grid(128)
+            P_, T_, S_ = torch.from_numpy(pts).to(dev), torch.from_numpy(tets).to(dev), torch.from_numpy(sdf).to(dev)
+            tv, tf = prim3d.marching_tetrahedras(P_, T_.clone(), S_)
+            t_mt = time_kernel(lambda: prim3d.marching_tetrahedras(P_, T_.clone(), S_), reps=5)
+            t_clone = time_kernel(lambda: T_.clone(), reps=5)
+            nT, nP, nV, nF = T_.shape[0], P_.shape[0], tv.shape[0], tf.shape[0]
+            b_mt = 32 * nT + 16 * nP + 12 * nV + 24 * nF
+            leg = {"ms": t_mt - t_clone, "T": nT, "P": nP, "V": nV, "F": nF, "algorithmic_bytes": b_mt,
+                   "achieved_gbs": b_mt / ((t_mt - t_clone) * 1e-3) / 1e9,
+                   "note": "prim3d.marching_tetrahedras on CUDA tensors (tets cloned per call: the call flips them in place; "
+                           "clone time subtracted)"}
+            ref_py = os.path.join(ROOT, "oracle", "_ref", "ref_marching_tetrahedras.py")
+            if os.path.exists(ref_py):
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("ref_marching_tetrahedras", ref_py)
+                rmt = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(rmt)
+                t_rmt = time_kernel(lambda: rmt.marching_tetrahedras(P_, T_.clone(), S_), reps=3)
+                leg["reference_torch_ms"] = t_rmt - t_clone
+                leg["speedup"] = (t_rmt - t_clone) / (t_mt - t_clone)
+            line["tets_kuhn128"] = leg
+            del P_, T_, S_, tv, tf
+        except Exception as exc:
+            line["tets_kuhn128"] = {"error": str(exc)[:200]}
+
         # ---- the multi-GPU workload (gyroid 2048^3) on this single GPU: the base of the strong-scaling claim ----
         try:
             torch.cuda.empty_cache()
