@@ -214,8 +214,17 @@ def main():
 
     launches_per_step = 2 + (1 if world > 1 and rank + 1 < world else 0)  # k_tile, k_faces (+halo import)
 
-    def step():
-        return sharded.marching_cubes_slab(slab, 0.0, x0, n)
+    if world == 1:
+        # one GPU: the reference-facing module itself, prim3d.libPrim3D.marching_cubes (pybind -> p3d_mc_extract)
+        import prim3d
+        box_lo, box_hi = [0.0, 0.0, 0.0], [float(n)] * 3
+
+        def step():
+            v, f = prim3d._C.marching_cubes(slab, 0.0, box_lo, box_hi)
+            return sharded.SlabMesh(v, f, 0, 0, v.shape[0], f.shape[0])
+    else:
+        def step():
+            return sharded.marching_cubes_slab(slab, 0.0, x0, n)
 
     for _ in range(args.warmup):
         out = step()
