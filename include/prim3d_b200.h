@@ -147,6 +147,20 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
                           size_t workspace_bytes, float *vertices, int64_t vertex_capacity,
                           int32_t *faces, int64_t face_capacity, int64_t *counts_host, void *stream);
 
+/* Batched small grids (the reference's own TODO, marching_cubes.cu:255-256): num_grids independent
+ * extractions queued back to back on `stream`, ONE host synchronisation for all of them.  A 66^3
+ * grid costs ~25 us of GPU time but ~3x that per call when every call waits for its own counts;
+ * here the wait is paid once per batch.  descs[i] / grids[i] as in p3d_mc_extract (any shapes;
+ * one `dtype` for the batch); `workspace` is shared, sized for the largest grid
+ * (p3d_mc_workspace_bytes); vertices[i] / faces[i] are per-grid buffers of speculative capacity
+ * with the semantics of p3d_mc_extract; counts_host = int64[2*num_grids] = {V_0, F_0, V_1, ...}.
+ * The pointer arrays are host arrays of device pointers.  A grid whose output did not fit is
+ * redone by the caller with p3d_mc_extract into exact buffers. */
+p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, const void *const *grids, int dtype,
+                                void *workspace, size_t workspace_bytes, float *const *vertices,
+                                const int64_t *vertex_capacities, int32_t *const *faces,
+                                const int64_t *face_capacities, int64_t *counts_host, void *stream);
+
 /* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
  * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: tile pass (classify,
  * count, look-back, vertices).  The face stage (scan over chunks + faces) is p3d_mc_faces itself. */

@@ -9,8 +9,8 @@ repository replaces: dense-grid marching cubes and marching tetrahedra.
 The reference-facing API is the sibling package `prim3d` (same names as the reference).
 There is no CPU implementation in this package; loading fails loudly if the library is unbuilt.
 """
-from .capi import (McDesc, abi_version, lib, marching_cubes_host, mc_count, mc_extract, mc_faces, mc_vertices,  # noqa: F401
+from .capi import (McDesc, abi_version, lib, marching_cubes_batch, marching_cubes_host, mc_count, mc_extract, mc_faces, mc_vertices,  # noqa: F401
                    mc_workspace_bytes)
 
-__all__ = ["McDesc", "abi_version", "lib", "marching_cubes_host", "mc_count", "mc_extract", "mc_faces", "mc_vertices",
+__all__ = ["McDesc", "abi_version", "lib", "marching_cubes_batch", "marching_cubes_host", "mc_count", "mc_extract", "mc_faces", "mc_vertices",
            "mc_workspace_bytes"]

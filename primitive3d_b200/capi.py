@@ -78,6 +78,8 @@ def lib():
         L.p3d_mc_extract_host.argtypes = [dp, vp, ctypes.c_int, i64, vp, i64, vp, i64, ctypes.POINTER(i64), vp, sz]
         L.p3d_mc_extract_host_arena_bytes.restype = sz
         L.p3d_mc_extract_host_arena_bytes.argtypes = [dp, ctypes.c_int, i64]
+        L.p3d_mc_extract_batch.restype = ctypes.c_int
+        L.p3d_mc_extract_batch.argtypes = [i64, vp, vp, ctypes.c_int, vp, sz, vp, vp, vp, vp, vp, vp]
         L.p3d_mc_faces.restype = ctypes.c_int
         L.p3d_mc_faces.argtypes = [dp, vp, vp, i64, vp]
         L.p3d_mc_debug_stage.restype = ctypes.c_int
@@ -230,6 +232,51 @@ def mc_extract(desc, grid, vertex_capacity=None, face_capacity=None):
     verts = mc_vertices(desc, grid, ws, V, vbuf)
     faces = fbuf[:F] if F <= face_capacity else mc_faces(desc, ws, F)
     return verts, faces, V, F
+
+
+def marching_cubes_batch(grids, thresh, lower=None, upper=None):
+    """Many (small) grids, one host synchronisation (p3d_mc_extract_batch): the extractions are queued back to
+    back and share one workspace.  grids: sequence of contiguous CUDA tensors [Rx,Ry,Rz] of ONE supported dtype on
+    one device (shapes may differ); lower / upper: None (each grid's own [0, shape] box) or one box for all.
+    -> list of (vertices float32 [V,3], faces int32 [F,3]).  A grid whose speculative buffers were too small is
+    redone on its own."""
+    grids = list(grids)
+    if not grids:
+        return []
+    dtype = _grid_ok(grids[0])
+    dev = grids[0].device
+    if any(_grid_ok(g) != dtype or g.device != dev for g in grids):
+        raise ValueError("a batch must have one dtype and one device")
+    n = len(grids)
+    descs = (McDesc * n)(*[McDesc.make(g.shape, thresh, lower, upper) for g in grids])
+    sizes = [_desc_sizes(d) for d in descs]
+    ws = torch.empty(max(s[0] for s in sizes), dtype=torch.uint8, device=dev)
+    vcaps, fcaps = [s[1] for s in sizes], [2 * s[1] for s in sizes]
+    # one allocation per output kind, carved into per-grid buffers (256-byte aligned starts)
+    pad = lambda rows: (rows * 12 + 255) // 256 * 256
+    voff, foff = [0], [0]
+    for v, f in zip(vcaps, fcaps):
+        voff.append(voff[-1] + pad(v))
+        foff.append(foff[-1] + pad(f))
+    vall = torch.empty(voff[-1], dtype=torch.uint8, device=dev)
+    fall = torch.empty(foff[-1], dtype=torch.uint8, device=dev)
+    ptrs = lambda vals: (ctypes.c_void_p * n)(*vals)
+    i64s = lambda vals: (ctypes.c_int64 * n)(*vals)
+    counts = (ctypes.c_int64 * (2 * n))()
+    with _on_device(dev):
+        check(lib().p3d_mc_extract_batch(n, descs, ptrs([g.data_ptr() for g in grids]), dtype, ws.data_ptr(), ws.numel(),
+                                         ptrs([vall.data_ptr() + o for o in voff[:-1]]), i64s(vcaps),
+                                         ptrs([fall.data_ptr() + o for o in foff[:-1]]), i64s(fcaps), counts, _stream()))
+    out = []
+    for i, g in enumerate(grids):
+        V, F = counts[2 * i], counts[2 * i + 1]
+        if V <= vcaps[i] and F <= fcaps[i]:
+            v = vall[voff[i]:voff[i] + 12 * V].view(torch.float32).view(V, 3)
+            f = fall[foff[i]:foff[i] + 12 * F].view(torch.int32).view(F, 3)
+        else:
+            v, f, _, _ = mc_extract(descs[i], g, V, F)
+        out.append((v, f))
+    return out
 
 
 def marching_cubes_host(grid, thresh, lower=None, upper=None, slab_planes=0, vertices_out=None, faces_out=None,

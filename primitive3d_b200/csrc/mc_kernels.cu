@@ -655,7 +655,7 @@ struct FaceScratch {
     uint2 rank[kFaceSlots * kRankStride];  // per word slot and mask q: {mask, id of its first crossing (+ vertex_id_base)}
     uint16_t cell[kCellCap];              // slot<<5 | bit
     uint32_t tri[kTriBatch];              // slot<<5 | bit | three entry nibbles << 12
-    unsigned long long gbase[16];         // index of the first face of each group of the (up to two) chunks in flight
+    unsigned long long gbase[32];         // index of the first face of each group of the chunks of the runs in flight
 };
 constexpr int kFaceSmemBytes = 256 * (int)sizeof(uint64_t) + kFaceWarps * (int)sizeof(FaceScratch);
 
@@ -667,7 +667,7 @@ __device__ __forceinline__ uint32_t corner_code(const uint4 &w, const uint4 &n, 
 
 __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
     k_faces(McGeom g, McWorkspace ws, int32_t vbase, int32_t *__restrict__ faces, unsigned long long face_capacity,
-            int vertex_base_from_header) {
+            int vertex_base_from_header, int gpt, uint32_t ntickets) {
     if (vertex_base_from_header) vbase += (int32_t)ws.header->vertex_base;  // multi-GPU: computed by k_apply_exchange
     // speculative launch (p3d_mc_extract): the buffer was sized before F was known; if it is too small nothing is
     // written and the caller runs the pass again with an exact buffer
@@ -700,31 +700,33 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
     const int h = lane & 1;  // which half of the piece
     const uint32_t lanes_below = (1u << lane) - 1u;
 
-    // ---- work distribution: chunks of kFaceChunk consecutive groups by ticket (the cost of a group follows the
-    // surface, so a static round-robin leaves SMs idle at the end); the ticket of the next chunk is taken a
-    // chunk ahead of its use.  The first face index of each group of a chunk is parked in shared memory
-    // (two chunks can be in the pipeline at once: slots 0-7 and 8-15 alternate). ----
-    const uint32_t nchunks = (uint32_t)g.nchunks;
+    // ---- work distribution: runs of `gpt` consecutive groups by ticket (the cost of a group follows the surface,
+    // so a static round-robin leaves SMs idle at the end); the next ticket is taken a run ahead of its use.  gpt is
+    // a whole chunk (8 groups) on large grids and 4, 2 or 1 on small ones, where spreading the groups over more warps
+    // matters more than sharing the chunk's prefix loads.  The first face index of each group of the run's chunk is
+    // parked in shared memory; up to three runs are in the pipeline at once, so four sets of slots rotate. ----
     uint32_t ticket_ahead = 0;
     auto take_ticket = [&]() {
         if (lane == 0) ticket_ahead = atomicAdd(&ws.header->ticket_faces, 1u);
     };
     take_ticket();
-    uint32_t chunk_id = 0, chunk_j = 0, chunk_n = 0, chunk_slot = 8;
+    uint32_t run_ticket = 0, chunk_j = 0, chunk_n = 0, chunk_slot = 0;
     bool exhausted = false;
     auto next_group = [&](uint32_t &slot) -> int64_t {
         if (chunk_j == chunk_n && !exhausted) {
-            chunk_id = __shfl_sync(kFull, ticket_ahead, 0);
-            if (chunk_id >= nchunks) {
+            run_ticket = __shfl_sync(kFull, ticket_ahead, 0);
+            if (run_ticket >= ntickets) {
                 exhausted = true;
             } else {
                 take_ticket();
-                const int64_t first_group = (int64_t)chunk_id * kFaceChunk;
+                const int64_t run_first = (int64_t)run_ticket * gpt;
+                const uint32_t chunk_id = (uint32_t)(run_first / kFaceChunk);
                 chunk_j = 0;
-                chunk_n = (uint32_t)(first_group + kFaceChunk < ngroups ? kFaceChunk : ngroups - first_group);
-                chunk_slot ^= 8u;
+                chunk_n = (uint32_t)(run_first + gpt < ngroups ? gpt : ngroups - run_first);
+                chunk_slot = ((chunk_slot & ~7u) + 8u) & 31u;            // next set of eight slots ...
+                chunk_slot += (uint32_t)(run_first % kFaceChunk);        // ... at the run's first group in its chunk
                 // everything in one batch of loads: my four counts, the rounds before, the chunks before in the round
-                const int64_t p0 = first_group * kFacePieces + 4 * lane;
+                const int64_t p0 = (int64_t)chunk_id * (kFaceChunk * kFacePieces) + 4 * lane;
                 uint4 n4 = make_uint4(0u, 0u, 0u, 0u);
                 if (p0 + 4 <= g.npieces) {
                     n4 = __ldg(reinterpret_cast<const uint4 *>(ws.nf + p0));
@@ -744,13 +746,13 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
                 const unsigned long long chunk_face = warp_sum64(acc);
                 const uint32_t mine = n4.x + n4.y + n4.z + n4.w, excl = warp_incl_scan(mine, lane) - mine;
                 // group j of the chunk = pieces 16 j .. 16 j + 15 = lanes 4 j .. 4 j + 3
-                if ((lane & 3) == 0) sc.gbase[chunk_slot + (lane >> 2)] = chunk_face + excl;
+                if ((lane & 3) == 0) sc.gbase[(chunk_slot & ~7u) + (lane >> 2)] = chunk_face + excl;
                 __syncwarp();
             }
         }
         if (exhausted) return -1;
         slot = chunk_slot + chunk_j;
-        return (int64_t)chunk_id * kFaceChunk + chunk_j++;
+        return (int64_t)run_ticket * gpt + chunk_j++;
     };
     auto group_counts = [&](int64_t gr) {  // triangle count of my piece of group gr
         const int64_t i = gr * kFacePieces + (lane >> 1);
@@ -1084,7 +1086,11 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     if (g.npieces <= 0) return;
     k_round_sums<<<(unsigned)g.nfrounds, kRoundTiles, 0, s>>>(g, ws);
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
-    const int64_t want = ((groups + kFaceChunk - 1) / kFaceChunk + kFaceWarps - 1) / kFaceWarps, cap = (int64_t)sm_count() * kFaceCtasPerSm;
+    const int64_t cap = (int64_t)sm_count() * kFaceCtasPerSm;
+    // groups per ticket: a whole chunk when there are at least two runs per resident warp, else fewer (small grids)
+    int gpt = kFaceChunk;
+    while (gpt > 1 && groups / gpt < 2 * cap * kFaceWarps) gpt /= 2;
+    const int64_t want = ((groups + gpt - 1) / gpt + kFaceWarps - 1) / kFaceWarps;
     static const bool attr = [] {
         cudaFuncSetAttribute(k_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaceSmemBytes);
         return true;
@@ -1093,7 +1099,8 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     cudaMemsetAsync(&ws.header->ticket_faces, 0, sizeof(unsigned int), s);
     k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces,
                                                                                          (unsigned long long)face_capacity,
-                                                                                         vertex_base_from_header ? 1 : 0);
+                                                                                         vertex_base_from_header ? 1 : 0, gpt,
+                                                                                         (uint32_t)((groups + gpt - 1) / gpt));
 }
 
 // Multi-GPU.  Export: the first plane's table entries (shard-local ids).  Import: install the next shard's

@@ -110,11 +110,18 @@ p3d::McEmitParams make_params(const p3d_mc_desc *desc, int64_t vertex_id_base) {
     return prm;
 }
 
-// One pinned 16-byte landing pad per host thread for the {V,F} readback.
-int64_t *pinned_counts() {
+// One pinned landing pad per host thread for the {V,F} readbacks (grown on demand for batches).
+int64_t *pinned_counts(size_t pairs = 1) {
     thread_local int64_t *buf = nullptr;
-    if (!buf && cudaHostAlloc(reinterpret_cast<void **>(&buf), 4 * sizeof(int64_t), cudaHostAllocPortable) != cudaSuccess)
-        buf = nullptr;
+    thread_local size_t cap = 0;
+    if (pairs > cap) {
+        if (buf) cudaFreeHost(buf);
+        cap = pairs < 64 ? 64 : pairs * 2;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&buf), cap * 2 * sizeof(int64_t), cudaHostAllocPortable) != cudaSuccess) {
+            buf = nullptr;
+            cap = 0;
+        }
+    }
     return buf;
 }
 
@@ -249,6 +256,51 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
     counts_host[1] = dst[1];
     if (counts_host[0] > INT32_MAX)
         return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract: vertex count exceeds the int32 face-index contract");
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, const void *const *grids, int dtype,
+                                void *workspace, size_t workspace_bytes, float *const *vertices,
+                                const int64_t *vertex_capacities, int32_t *const *faces, const int64_t *face_capacities,
+                                int64_t *counts_host, void *stream) {
+    if (num_grids < 0) return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: negative batch size");
+    if (num_grids == 0) return P3D_OK;
+    if (!descs || !grids || !workspace || !vertices || !vertex_capacities || !faces || !face_capacities || !counts_host)
+        return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: null pointer");
+    if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: unknown dtype");
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: workspace must be 256-byte aligned");
+    int64_t *pin = pinned_counts((size_t)num_grids);
+    if (!pin) return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: pinned allocation failed");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int64_t i = 0; i < num_grids; ++i) {  // validate everything before anything is queued
+        p3d::McGeom g;
+        if (!make_geom(&descs[i], &g) || descs[i].rx != descs[i].owned_x || descs[i].global_rx < 1 || !grids[i])
+            return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: invalid descriptor or grid");
+        if (make_layout(g).total > workspace_bytes) return fail(P3D_ERR_WORKSPACE, "p3d_mc_extract_batch: workspace too small");
+        if (vertex_capacities[i] < 0 || face_capacities[i] < 0 || (vertex_capacities[i] && !vertices[i]) ||
+            (face_capacities[i] && !faces[i]))
+            return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: capacity without a buffer");
+    }
+    // The grids run one after the other on the stream and share the workspace (a grid's face pass has finished
+    // with it before the next grid's memset starts); the host waits once, for all the counts.
+    for (int64_t i = 0; i < num_grids; ++i) {
+        p3d::McGeom g;
+        make_geom(&descs[i], &g);
+        const Layout l = make_layout(g);
+        const p3d::McWorkspace ws = bind(workspace, l);
+        const p3d::McEmitParams prm = make_params(&descs[i], 0);
+        P3D_CUDA(cudaMemsetAsync(workspace, 0, l.zero_end, s));
+        p3d::launch_tile_pass(grids[i], dtype, g, ws, prm, vertices[i], vertex_capacities[i], 0, s);
+        if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_extract_batch: ") + p3d::tile_pass_error());
+        if (faces[i]) p3d::launch_faces(g, ws, prm, faces[i], face_capacities[i], false, s);
+        P3D_CUDA(cudaMemcpyAsync(pin + 2 * i, &ws.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    }
+    P3D_CUDA(cudaGetLastError());
+    P3D_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < 2 * num_grids; ++i) counts_host[i] = pin[i];
+    for (int64_t i = 0; i < num_grids; ++i)
+        if (counts_host[2 * i] > INT32_MAX)
+            return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract_batch: vertex count exceeds the int32 face-index contract");
     return P3D_OK;
 }
 

@@ -230,6 +230,26 @@ def test_host_streamed_extraction_equals_single_shot(shape, planes, dtype):
     assert torch.equal(v2, v) and torch.equal(f2, f)
 
 
+def test_batched_small_grids_equal_one_by_one():
+    """p3d_mc_extract_batch: many small grids queued back to back, one host wait; every mesh equals the one the
+    single call gives (including a grid dense enough to overflow its speculative buffers, and an empty one)."""
+    from primitive3d_b200 import capi
+    shapes = [(66, 66, 66), (17, 33, 65), (2, 2, 2), (40, 8, 130), (16, 16, 16), (9, 9, 384)]
+    grids = [torch.from_numpy(inputs.noise(s, 40 + i)).cuda() for i, s in enumerate(shapes)]
+    grids[4] = torch.full((16, 16, 16), -1.0, device="cuda")                     # empty mesh
+    grids[0] = torch.from_numpy(np.ascontiguousarray(bunny())).cuda()             # smooth: fits the speculative buffers
+    out = capi.marching_cubes_batch(grids, 0.0)
+    assert len(out) == len(grids)
+    for g, (v, f) in zip(grids, out):
+        v0, f0 = capi.marching_cubes(g, 0.0)
+        assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0)
+    assert out[4][0].shape == (0, 3) and out[4][1].shape == (0, 3)
+    one_box = capi.marching_cubes_batch(grids[:2], 0.1, [-1.0, -1.0, -1.0], [1.0, 2.0, 3.0])
+    v0, f0 = capi.marching_cubes(grids[1], 0.1, [-1.0, -1.0, -1.0], [1.0, 2.0, 3.0])
+    assert torch.equal(one_box[1][0], v0) and torch.equal(one_box[1][1], f0)
+    assert capi.marching_cubes_batch([], 0.0) == []
+
+
 def test_unsupported_dtype_is_cast_by_the_wrapper():
     import prim3d
     g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
