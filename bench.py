@@ -383,6 +383,19 @@ def main():
                 line["reference_cuda_gyroid512"] = {"reference_ms": t_ref, "ours_ms": t_our, "speedup": t_ref / t_our,
                                                     "note": "reference marching_cubes.cu compiled unmodified for sm_100a"}
                 del g512
+                # the reference's own example sizes (BASELINE configs[0], [1]): latency-bound, not roofline cases
+                from oracle import inputs as oin   # input generators only
+                small = {"sphere128": torch.from_numpy(oin.sphere_int64(128).astype(np.float32)).to(dev),
+                         "bunny66": torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "mc_bunny66.npz"))["grid"]).to(dev)}
+                small["bunny256"] = torch.nn.functional.interpolate(small["bunny66"][None, None], size=(256,) * 3,
+                                                                    mode="trilinear", align_corners=True)[0, 0].contiguous()
+                line["reference_cuda_examples"] = {}
+                for name, gs in small.items():
+                    box = [float(v) for v in gs.shape]
+                    t_r = time_kernel(lambda: ref.marching_cubes(gs, 0.0, [0, 0, 0], box), reps=10)
+                    t_o = time_kernel(lambda: prim3d._C.marching_cubes(gs, 0.0, [0, 0, 0], box), reps=10)
+                    line["reference_cuda_examples"][name] = {"reference_ms": t_r, "ours_ms": t_o, "speedup": t_r / t_o}
+                del small
             except Exception as exc:  # the comparison is informative only
                 line["reference_cuda_gyroid512"] = {"error": str(exc)[:200]}
 
