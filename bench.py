@@ -212,7 +212,8 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     torch.cuda.synchronize()
 
-    launches_per_step = 2 + (1 if world > 1 and rank + 1 < world else 0)  # k_tile, k_faces (+halo import)
+    # our kernels per step: k_tile, k_round_sums, k_faces (+ k_export_exchange, k_apply_exchange on several GPUs)
+    launches_per_step = 3 if world == 1 else 5
 
     if world == 1:
         # one GPU: the reference-facing module itself, prim3d.libPrim3D.marching_cubes (pybind -> p3d_mc_extract)
