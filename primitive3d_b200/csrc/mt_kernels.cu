@@ -252,14 +252,37 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *data, int64_t n) {
     }
 }
 
+template <bool FUSED_SCAN>
 __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
                                                            int64_t n, int shift, const uint32_t *__restrict__ ghist,
                                                            int nblocks) {
     __shared__ uint32_t s_cnt[kThreads / 32][256];
+    __shared__ uint32_t s_digit[kThreads / 32];
     sort_tile_counts(in, n, shift, s_cnt);
     {  // per-warp output bases: global digit base of this tile + the lower warps' counts
         const int d = threadIdx.x;
-        uint32_t run = ghist[(int64_t)d * nblocks + blockIdx.x];
+        uint32_t run;
+        if (FUSED_SCAN) {
+            // few tiles: every CTA derives its offsets from the raw per-tile counts itself (keys of smaller digits +
+            // keys of my digit in earlier tiles) instead of a single-CTA scan kernel between the two passes
+            const uint32_t *row = ghist + (int64_t)d * nblocks;
+            uint32_t before = 0, total = 0;
+#pragma unroll 4
+            for (int b = 0; b < nblocks; ++b) {
+                const uint32_t c = row[b];
+                total += c;
+                if (b < (int)blockIdx.x) before += c;
+            }
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const uint32_t incl = warp_incl_scan(total, lane);
+            if (lane == 31) s_digit[warp] = incl;
+            __syncthreads();
+            uint32_t lower = 0;
+            for (int w = 0; w < warp; ++w) lower += s_digit[w];
+            run = lower + incl - total + before;
+        } else {
+            run = ghist[(int64_t)d * nblocks + blockIdx.x];
+        }
         for (int w = 0; w < kThreads / 32; ++w) {
             const uint32_t c = s_cnt[w][d];
             s_cnt[w][d] = run;
@@ -539,8 +562,12 @@ p3d_status p3d_mt_index(const int64_t *tets, int64_t num_tets, int64_t num_point
         for (int sh = 0; sh < bits; sh += 8) {
             const int shift = half * 32 + sh;
             k_sort_hist<<<l.sort_blocks, kThreads, 0, s>>>(src, ne, shift, ghist, l.sort_blocks);
-            k_sort_scan<<<1, 1024, 0, s>>>(ghist, (int64_t)l.sort_blocks * 256);
-            k_sort_scatter<<<l.sort_blocks, kThreads, 0, s>>>(src, dst, ne, shift, ghist, l.sort_blocks);
+            if (l.sort_blocks <= 512) {
+                k_sort_scatter<true><<<l.sort_blocks, kThreads, 0, s>>>(src, dst, ne, shift, ghist, l.sort_blocks);
+            } else {
+                k_sort_scan<<<1, 1024, 0, s>>>(ghist, (int64_t)l.sort_blocks * 256);
+                k_sort_scatter<false><<<l.sort_blocks, kThreads, 0, s>>>(src, dst, ne, shift, ghist, l.sort_blocks);
+            }
             uint64_t *t = src;
             src = dst;
             dst = t;

@@ -61,6 +61,21 @@ def test_noisy_sdf_many_valid_tets():
     assert np.array_equal(f, of) and np.array_equal(ti, oti) and np.array_equal(tets_after, o_tets)
 
 
+def test_noisy_sdf_large_sort():
+    """~3 M crossing-edge keys: more than 512 radix-sort tiles, i.e. the pass with the separate scan kernel (the
+    smaller cases above take the pass with the scan fused into the scatter kernel)."""
+    pts, tets, _ = inputs.kuhn_tet_grid(56)
+    sdf = np.random.default_rng(6).uniform(-1, 1, len(pts)).astype(np.float32)
+    v, f, ti, e, tets_after = run_capi(pts, tets, sdf)
+    o_tets = tets.copy()
+    ov, of, oti = mt.marching_tetrahedras(pts, o_tets, sdf, True)
+    per_tet = np.unique(oti, return_counts=True)[1]   # 1 or 2 triangles per valid tet: 3 or 4 crossing edges
+    assert 3 * int((per_tet == 1).sum()) + 4 * int((per_tet == 2).sum()) > 512 * 4096
+    assert np.array_equal(tets_after, o_tets)
+    assert np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+    assert np.array_equal(f, of) and np.array_equal(ti, oti)
+
+
 def test_python_entry_point_contract():
     """prim3d.marching_tetrahedras: CUDA and CPU tensors, in-place mutation, return_tet_idx,
     empty result (reference marching_tetrahedras.py:89-94,148,225-235)."""
