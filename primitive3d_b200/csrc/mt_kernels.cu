@@ -30,7 +30,7 @@ namespace p3d {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTetsPerThread = 8;
+constexpr int kTetsPerThread = 16;
 constexpr int kTileTets = kThreads * kTetsPerThread;  // compaction tile
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kThreads * kSortItems;      // radix-sort tile (4096 keys)
@@ -159,9 +159,18 @@ __global__ void __launch_bounds__(kThreads) k_mt_compact(const int64_t *__restri
         uint32_t code[kTetsPerThread];
         unsigned long long mine = 0;  // n1 in bits 0..30, n2 in bits 31..61
         uint32_t nkeys = 0;
+        static_assert(kTetsPerThread == 16, "one 16-byte load of codes per thread");
+        if (t0 + kTetsPerThread <= T) {
+            const uint4 c4 = *reinterpret_cast<const uint4 *>(codes + t0);  // t0 is a multiple of 16
+            const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int j = 0; j < kTetsPerThread; ++j) code[j] = (cw[j >> 2] >> (8 * (j & 3))) & 255u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kTetsPerThread; ++j) code[j] = (t0 + j < T) ? codes[t0 + j] : 0u;
+        }
 #pragma unroll
         for (int j = 0; j < kTetsPerThread; ++j) {
-            code[j] = (t0 + j < T) ? codes[t0 + j] : 0u;
             const uint32_t nt = num_tri(code[j]);
             mine += (nt == 1u ? 1ull : 0ull) + (nt == 2u ? (1ull << 31) : 0ull);
             nkeys += nt == 1u ? 3u : (nt == 2u ? 4u : 0u);
