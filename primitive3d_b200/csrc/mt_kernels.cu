@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restric
                                                           ClassifyCounters *counters) {
     unsigned long long n1 = 0, n2 = 0;
     longlong2 *t2 = reinterpret_cast<longlong2 *>(tets);
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
-        const longlong2 lo = t2[2 * t], hi = t2[2 * t + 1];
+    auto one = [&](int64_t t, longlong2 lo, longlong2 hi) {
         int64_t i0 = lo.x, i1 = lo.y;
         const int64_t i2 = hi.x, i3 = hi.y;
         const double p0x = __ldg(pts + 3 * i0), p0y = __ldg(pts + 3 * i0 + 1), p0z = __ldg(pts + 3 * i0 + 2);
@@ -99,7 +98,17 @@ __global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restric
         const uint32_t nt = num_tri(code);
         n1 += nt == 1u;
         n2 += nt == 2u;
+    };
+    // two tets per iteration, their index loads issued together: the dependent gathers of one overlap the other's
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + stride < T; t += 2 * stride) {
+        const longlong2 lo0 = t2[2 * t], hi0 = t2[2 * t + 1];
+        const longlong2 lo1 = t2[2 * (t + stride)], hi1 = t2[2 * (t + stride) + 1];
+        one(t, lo0, hi0);
+        one(t + stride, lo1, hi1);
     }
+    if (t < T) one(t, t2[2 * t], t2[2 * t + 1]);
     n1 = warp_sum64(n1);
     n2 = warp_sum64(n2);
     __shared__ unsigned long long s1[kThreads / 32], s2[kThreads / 32];
