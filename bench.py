@@ -104,9 +104,9 @@ class ClockSampler:
 
 def gyroid_cuda(n, x0, x1, device, periods=8):
     """Gyroid(N, P) planes [x0, x1) built on the device from the two fp32 tables; same separately
-    rounded fp32 ops as oracle.inputs.gyroid (bit-identical, tests/test_mc_cuda.py)."""
+    rounded fp32 ops as workloads.gyroid (bit-identical, tests/test_mc_cuda.py)."""
     import torch
-    from oracle import inputs  # table generator only (numpy sin/cos), not a compute path
+    from primitive3d_b200 import workloads as inputs  # table generator only (numpy sin/cos)
     s, c = (torch.from_numpy(t).to(device) for t in inputs.gyroid_tables(n, periods))
     g = s[x0:x1, None, None] * c[None, :, None]
     g = g + s[None, :, None] * c[None, None, :]
@@ -385,7 +385,7 @@ def main():
                                                     "note": "reference marching_cubes.cu compiled unmodified for sm_100a"}
                 del g512
                 # the reference's own example sizes (BASELINE configs[0], [1]): latency-bound, not roofline cases
-                from oracle import inputs as oin   # input generators only
+                from primitive3d_b200 import workloads as oin   # input generators only
                 small = {"sphere128": torch.from_numpy(oin.sphere_int64(128).astype(np.float32)).to(dev),
                          "bunny66": torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "mc_bunny66.npz"))["grid"]).to(dev)}
                 small["bunny256"] = torch.nn.functional.interpolate(small["bunny66"][None, None], size=(256,) * 3,
@@ -402,7 +402,7 @@ def main():
 
         # ---- marching tetrahedra, BASELINE configs[3] (Kuhn tet grid 128^3), beside the reference's torch ops on this GPU ----
         try:
-            from oracle import inputs as oin   # input generator only
+            from primitive3d_b200 import workloads as oin   # input generator only
             pts, tets, sdf = oin.kuhn_tet_grid(128)
             P_, T_, S_ = torch.from_numpy(pts).to(dev), torch.from_numpy(tets).to(dev), torch.from_numpy(sdf).to(dev)
             tv, tf = prim3d.marching_tetrahedras(P_, T_.clone(), S_)

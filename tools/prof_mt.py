@@ -1,7 +1,7 @@
 import sys, torch, time
 sys.path.insert(0, '.')
 import prim3d
-from oracle import inputs
+from primitive3d_b200 import workloads as inputs
 pts, tets, sdf = inputs.kuhn_tet_grid(128)
 P, T, S = torch.from_numpy(pts).cuda(), torch.from_numpy(tets).cuda(), torch.from_numpy(sdf).cuda()
 for _ in range(3):

@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import inputs  # noqa: E402  (input generators only)
+from primitive3d_b200 import workloads as inputs  # noqa: E402  (input generators only)
 from primitive3d_b200 import capi  # noqa: E402
 
 
