@@ -117,6 +117,30 @@ def test_cpu_mode_wraps_mcubes_and_no_silent_fallback():
             prim3d.marching_cubes(torch.tensor(g), 0)
         with pytest.raises(RuntimeError, match="CUDA"):
             prim3d.marching_tetrahedras(torch.zeros(4, 3), torch.zeros(1, 4, dtype=torch.long), torch.zeros(4))
+        from primitive3d_b200 import capi
+        with pytest.raises(RuntimeError, match="CUDA"):       # host-resident grids still need the device
+            capi.marching_cubes_host(torch.zeros(8, 8, 8), 0.0)
+        with pytest.raises(ValueError):                       # and the batch / staged calls want CUDA tensors
+            capi.marching_cubes_batch([torch.zeros(8, 8, 8)], 0.0)
+
+
+def test_host_and_batch_entry_points_validate_their_arguments():
+    import torch
+    from primitive3d_b200 import capi
+    with pytest.raises(ValueError):
+        capi.marching_cubes_host(torch.zeros(8, 8, 16)[:, :, ::2], 0.0)      # not contiguous
+    with pytest.raises(ValueError):
+        capi.marching_cubes_host(torch.zeros(8, 8), 0.0)                      # not 3-D
+    with pytest.raises(ValueError):
+        capi.marching_cubes_host(torch.zeros(8, 8, 8, dtype=torch.int8), 0.0)  # element type the kernels do not read
+    assert capi.marching_cubes_batch([], 0.0) == []
+    # descriptor-only helpers work without a device
+    d = capi.McDesc.make((1024, 1024, 1024), 0.0)
+    L = capi.lib()
+    import ctypes
+    arena = L.p3d_mc_extract_host_arena_bytes(ctypes.byref(d), 0, 0)
+    assert 2 * 65 * 4 * 1024 ** 2 < arena < 2 * 1024 ** 3          # two 65-plane slabs + workspaces + output buffers
+    assert L.p3d_mc_exchange_words(ctypes.byref(d)) == 1024 * 8 * 4 + 4
 
 
 def test_save_mesh_ply_bytes(tmp_path):
