@@ -38,6 +38,20 @@ def test_exclusive_offsets():
     assert exclusive_offsets(counts, 2) == (5, 9, 12, 22)
 
 
+def test_unpack_counts_reads_the_payload_tails():
+    """Host side of the device-driven exchange: every payload is [table words ... , V lo, V hi, F lo, F hi]."""
+    from primitive3d_b200.sharded import exclusive_offsets, unpack_counts
+    world, words = 3, 12 + 4
+    gathered = torch.zeros(world * words, dtype=torch.int32)
+    expect = [(5, 9), (2 ** 33 + 1, 2 ** 35 + 7), (0, 0)]
+    for r, (v, f) in enumerate(expect):
+        gathered.view(world, words)[r, :12] = 100 * r + torch.arange(12, dtype=torch.int32)
+        gathered.view(world, words)[r, 12:] = torch.tensor([v, f], dtype=torch.int64).view(torch.int32)
+    counts = unpack_counts(gathered, world, words)
+    assert counts == expect
+    assert exclusive_offsets(counts, 2) == (5 + 2 ** 33 + 1, 9 + 2 ** 35 + 7, 5 + 2 ** 33 + 1, 9 + 2 ** 35 + 7)
+
+
 def test_count_exchange_world_size_2_gloo():
     import json
     import socket
