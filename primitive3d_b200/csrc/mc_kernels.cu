@@ -157,16 +157,17 @@ __device__ __forceinline__ bool scan_prefix(const McScan &sc, uint32_t item, int
 // Shared memory of a CTA:
 //   stage      fp32 samples of a tile: rows (xi, yi) of 0..8 x 0..8, kBoxZ samples each (TMA box)
 //   sbits      [81][8] words: inside bits of every staged row (word 4, bit 0 = the halo sample)
-//   piece      [64] vertex count of each owned (row, piece)
-//   list, dt   per warp: the crossing edges of the warp's 8 rows (axis<<13 | row<<7 | z) and their
-//              interpolation parameters
+//   piece, nfp [64] vertex / triangle count of each owned (row, piece)
+//   ent, dt    ring of the pending crossing edges (axis<<13 | row<<7 | z) and their interpolation parameters:
+//              the tiles whose first vertex id is not known yet (a warp's 8 rows are a contiguous range)
+//   q, prel    the pending tiles and their table entries, relative to the tile
 // A thread owns bit word (row r = tid>>2, word w = tid&3) of the tile in the count phase; a warp owns the 8
 // rows of one plane, whose vertices are a contiguous id range of the tile.
 //
 // Per tile: bits -> counts -> tile scan -> publish count -> per warp: compact edges, interpolate dt from the
 // staged samples -> the stage is free: the NEXT tile's TMA load is issued -> wait for the tile's first
-// vertex id -> write vertices (position = integer corner + dt on one axis) and the table entries.  The
-// load of the next tile and the wait for the scan overlap.
+// vertex id (asked for without blocking, one iteration later) -> write vertices (position = integer corner + dt
+// on one axis) and the table entries.  The load of the next tile and the wait for the scan overlap.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRing = 1408;     // pending crossing edges of a CTA (6 bytes each): ~4.5 tiles of the gyroid case
 constexpr int kQueue = 4;       // pending tiles of a CTA

@@ -4,17 +4,19 @@
 // src/prim3d/Utility/marching_cubes.cu:4-209 (reference) with a design that reads the fp32
 // grid ONCE and carries 1 bit per sample (+ 16 bytes per 128 samples) between two passes:
 //
-//   pass A  k_tile    persistent CTAs walk 8x8x128-sample tiles (+1 halo in x, y, z) that TMA
-//                     (cp.async.bulk.tensor, 2-stage mbarrier ring) stages in shared memory.
-//                     Per tile: inside bits (value > thresh, marching_cubes.cu:25) by ballot,
-//                     crossing masks and triangle counts per 32-sample word, a single-pass
-//                     decoupled look-back over tiles for the tile's first vertex id, then the
-//                     vertices themselves, interpolated from the staged fp32 samples in the
-//                     reference's operation order (marching_cubes.cu:105-109, :298).
+//   pass A  k_tile    persistent CTAs (four per SM, one staged tile each) walk 8x8x128-sample tiles
+//                     (+1 halo in x, y, z) that TMA (cp.async.bulk.tensor.3d, mbarrier) stages in
+//                     shared memory.  Per tile: inside bits (value > thresh, marching_cubes.cu:25), a
+//                     thread per 32-sample word; crossing masks per word; triangle counts from
+//                     popcounts of the edge masks (crossed edges - 2 per loop) with a table lookup
+//                     only for cells with an ambiguous face; a two-level single-pass scan over
+//                     tiles for the tile's first vertex id, then the vertices themselves,
+//                     interpolated from the staged fp32 samples in the reference's operation
+//                     order (marching_cubes.cu:105-109, :298).
 //                     Side products: bit words, one 16-byte table entry per (row, 128-sample
 //                     piece) = first id of its x-/y-/z-edge vertices + its triangle count.
 //                     Triangle counts are also summed (RED) per chunk of 128 consecutive (row, piece)
-//                     pairs and per round of 256 chunks, in voxel-major order.
+//                     pairs in voxel-major order; k_round_sums adds them per round of 256 chunks.
 //   pass B  k_faces   warps take chunks by ticket; a chunk's first face index is the sum of the
 //                     rounds before its round and of the chunks before it in its round (one batch
 //                     of loads of final data: no scan kernel, no CUB/thrust, no waiting).  A lane
