@@ -641,10 +641,7 @@ constexpr uint64_t kEdgeToEntry = (0ull << 0) | (3ull << 4) | (5ull << 8) | (1ul
                                   (13ull << 24) | (9ull << 28) | (2ull << 32) | (4ull << 36) | (7ull << 40) |
                                   (6ull << 44);
 constexpr int kFaceWarps = 4;
-#ifndef P3D_FACE_CTAS
-#define P3D_FACE_CTAS 6
-#endif
-constexpr int kFaceCtasPerSm = P3D_FACE_CTAS;
+constexpr int kFaceCtasPerSm = 6;   // 79 registers x 128 threads and 34 KB of shared memory per CTA
 static_assert(kFacePieces * kFaceChunk == 128, "a chunk is 4 pieces per lane");
 constexpr int kFaceSlots = 64;     // bit words per warp iteration
 constexpr int kCellCap = 256;
