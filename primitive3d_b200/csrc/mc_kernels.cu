@@ -453,8 +453,11 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         }
         const uint32_t tot = __shfl_sync(kFull, inc, lane | 3);
         const uint32_t exw = inc - cnt;
-        nf += __shfl_xor_sync(kFull, nf, 1);
-        nf += __shfl_xor_sync(kFull, nf, 2);
+        // triangles of the four words of my (row, piece), one byte each (<= 160): what the face pass reads per word
+        uint32_t nfw = nf << (8 * w);
+        nfw += __shfl_xor_sync(kFull, nfw, 1);
+        nfw += __shfl_xor_sync(kFull, nfw, 2);
+        nf = __dp4a(nfw, 0x01010101u, 0u);  // of the piece
         if (w == 0) {
             S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
             S.nfp[r] = (uint16_t)nf;  // <= 640
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const int64_t grow = (int64_t)x * ry + y;  // my row of the grid
         if (mode == 0) {
             if (x < rx && y < ry) ws.bits[grow * bstride + 4 * p + w] = A;
-            if (own && w == 0) ws.nf[grow * np + p] = nf;
+            if (own && w == 0) ws.nf[grow * np + p] = nfw;
             // the halo plane of a slab sits one past the last x-block when owned_x is a multiple of 8
             if (tid < 32 && x0 + kTileX == ox && ox < rx && y0 + (tid >> 2) < ry)
                 ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * bstride + 4 * p + (tid & 3)] =
@@ -742,7 +745,9 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
 #pragma unroll 4
                 for (uint32_t r = lane; r < round; r += 32) acc += __ldg(ws.fround_sum + r);
                 const unsigned long long chunk_face = warp_sum64(acc);
-                const uint32_t mine = n4.x + n4.y + n4.z + n4.w, excl = warp_incl_scan(mine, lane) - mine;
+                const uint32_t mine = __dp4a(n4.x, 0x01010101u, 0u) + __dp4a(n4.y, 0x01010101u, 0u) +
+                                      __dp4a(n4.z, 0x01010101u, 0u) + __dp4a(n4.w, 0x01010101u, 0u);
+                const uint32_t excl = warp_incl_scan(mine, lane) - mine;
                 // group j of the chunk = pieces 16 j .. 16 j + 15 = lanes 4 j .. 4 j + 3
                 if ((lane & 3) == 0) sc.gbase[(chunk_slot & ~7u) + (lane >> 2)] = chunk_face + excl;
                 __syncwarp();
@@ -752,9 +757,9 @@ __global__ void __launch_bounds__(kFaceWarps * 32, kFaceCtasPerSm)
         slot = chunk_slot + chunk_j;
         return (int64_t)run_ticket * gpt + chunk_j++;
     };
-    auto group_counts = [&](int64_t gr) {  // triangle count of my piece of group gr
+    auto group_counts = [&](int64_t gr) {  // triangle count of my piece of group gr (the tile pass stores a byte per word)
         const int64_t i = gr * kFacePieces + (lane >> 1);
-        return (gr >= 0 && i < g.npieces) ? __ldg(ws.nf + i) : 0u;
+        return (gr >= 0 && i < g.npieces) ? __dp4a(__ldg(ws.nf + i), 0x01010101u, 0u) : 0u;
     };
 
     // ---- everything a group reads from global memory, issued as one batch (a group ahead of its use) ----
@@ -1084,6 +1089,10 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
                   bool vertex_base_from_header, cudaStream_t s) {
     if (g.npieces <= 0) return;
     k_round_sums<<<(unsigned)g.nfrounds, kRoundTiles, 0, s>>>(g, ws);
+    if (faces_rows_applicable(g)) {
+        launch_faces_rows(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
+        return;
+    }
     const int64_t groups = (g.npieces + kFacePieces - 1) / kFacePieces;
     const int64_t cap = (int64_t)sm_count() * kFaceCtasPerSm;
     // groups per ticket: a whole chunk when there are at least two runs per resident warp, else fewer (small grids)

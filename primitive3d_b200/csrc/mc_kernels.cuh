@@ -83,7 +83,7 @@ struct McWorkspace {
     unsigned long long *fround_sum;  // [nfrounds] triangles of each round of 256 chunks (k_tile, RED)
     uint4 *ptab;                   // [rx*ry*np] {vx, vy, vz, nf}: ids of the piece's first x-/y-/z-edge vertex (relative to
                                    // the tile until the tile's first id is known, absolute after the tile pass)
-    uint32_t *nf;                  // [npieces] triangles per piece
+    uint32_t *nf;                  // [npieces] triangles of the four bit words of each piece, one byte per word (<= 160)
     uint32_t *bits;                // [rx*ry][4*np] inside bits, 32 samples per word
 };
 
@@ -104,6 +104,11 @@ void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWork
 // vertex_base_from_header: add header->vertex_base (launch_apply_exchange) to every face index
 void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
                   bool vertex_base_from_header, cudaStream_t s);
+// Row-streaming form of the face pass (mc_faces_rows.cu), for rows of 17..128 bit words; launch_faces uses it
+// when it applies.
+bool faces_rows_applicable(const McGeom &g);
+void launch_faces_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
+                       bool vertex_base_from_header, cudaStream_t s);
 // Multi-GPU exchange without the host: `out` = this shard's first-plane table + {V, F} (two int64) appended;
 // `gathered` = the all-gather of every shard's `out` ([world][words + 4] int32).
 void launch_export_exchange(uint32_t *out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);

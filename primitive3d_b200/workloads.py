@@ -35,9 +35,37 @@ def sphere_int64(n=200):
     return (X - 50) ** 2 + (Y - 50) ** 2 + (Z - 50) ** 2 - 25 ** 2
 
 
+def upsample_trilinear(grid, n):
+    """`grid` resampled to n^3 by separable linear interpolation with corner alignment (sample i of the
+    output sits at i * (n_in - 1) / (n - 1) of the input), every operation a separately rounded fp32
+    one in a fixed order: reproducible bit for bit wherever numpy runs.  BASELINE's "bunny SDF at 256^3"
+    is upsample_trilinear(bunny66, 256) (the mesh the reference sampled its grid from is not available;
+    SURVEY.md section 8d config 2)."""
+    g = np.ascontiguousarray(grid, dtype=np.float32)
+    for axis in range(3):
+        m = g.shape[axis]
+        pos = (np.arange(n, dtype=np.float32) * np.float32(m - 1)) / np.float32(n - 1)
+        i0 = np.minimum(np.floor(pos).astype(np.int64), m - 2)
+        w = (pos - i0.astype(np.float32)).astype(np.float32)
+        shape = [1, 1, 1]
+        shape[axis] = n
+        w = w.reshape(shape)
+        a, b = np.take(g, i0, axis=axis), np.take(g, i0 + 1, axis=axis)
+        g = ((a * (np.float32(1.0) - w)).astype(np.float32) + (b * w).astype(np.float32)).astype(np.float32)
+    return np.ascontiguousarray(g)
+
+
 def noise(shape, seed):
     rng = np.random.default_rng(seed)
     return rng.uniform(-1.0, 1.0, size=shape).astype(np.float32)
+
+
+def waves(shape, periods=(1.5, 2.5, 3.5)):
+    """Smooth non-cubic field (a sum of three sines, fp32): sheet-like surfaces at any shape, no RNG."""
+    ax = [np.sin((2.0 * np.pi * p / n) * (np.arange(n, dtype=np.float64) + 0.25)).astype(np.float32)
+          for n, p in zip(shape, periods)]
+    g = (ax[0][:, None, None] + ax[1][None, :, None]).astype(np.float32)
+    return np.ascontiguousarray((g + ax[2][None, None, :]).astype(np.float32))
 
 
 def ties(shape, seed):

@@ -1,5 +1,5 @@
-"""The reference's own example scripts, byte-unchanged (staged from /root/reference/examples
-into oracle/_ref/examples by oracle/build_ref.py), must run against this repository's `prim3d`.
+"""The reference's own example scripts, byte-unchanged (examples/ in this tree: the acceptance
+fixtures BASELINE.json names), must run against this repository's `prim3d`.
 Their asserts are the only tests the reference has (examples/sphere.py:27-30,
 examples/bunny_sdf.py:28-31)."""
 import os
@@ -10,14 +10,13 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXAMPLES = os.path.join(ROOT, "oracle", "_ref", "examples")
+EXAMPLES = os.path.join(ROOT, "examples")
 
 
 @pytest.mark.parametrize("script", ["sphere.py", "bunny_sdf.py", "sphere_tetrahedra.py"])
 def test_reference_example_runs_unchanged(script, tmp_path):
     path = os.path.join(EXAMPLES, script)
-    if not os.path.exists(path):
-        pytest.skip("oracle/_ref/examples not staged (needs /root/reference at build time)")
+    assert os.path.exists(path)
     env = dict(os.environ)
     # `mcubes` (PyMCubes) is a third-party dependency of the examples that is not installable
     # here; the PyMCubes-compatible stand-in is put on the path for them.
@@ -29,3 +28,4 @@ def test_reference_example_runs_unchanged(script, tmp_path):
         assert "#vertices=" in out.stdout and "#triangles=" in out.stdout
     produced = {"sphere.py": "sphere.ply", "bunny_sdf.py": "bunny.ply", "sphere_tetrahedra.py": "sphere_tetrahedra.ply"}
     assert os.path.getsize(os.path.join(tmp_path, produced[script])) > 1000
+

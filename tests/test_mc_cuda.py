@@ -36,6 +36,7 @@ CASES = {
     "sphere128": (lambda: inputs.sphere_int64(128).astype(np.float32), 0.0, None, None),
     "sphere200": (lambda: inputs.sphere_int64(200).astype(np.float32), 0.0, None, None),
     "bunny66": (bunny, 0.0, None, None),
+    "bunny256": (lambda: inputs.upsample_trilinear(bunny(), 256), 0.0, None, None),  # BASELINE configs[1]
     "gyroid128": (lambda: inputs.gyroid(128), 0.0, None, None),
     "gyroid256": (lambda: inputs.gyroid(256), 0.0, None, None),
     "noise33_s0": (lambda: inputs.noise((33, 33, 33), 0), 0.0, None, None),
@@ -46,6 +47,14 @@ CASES = {
     "noise_long_rows": (lambda: inputs.noise((3, 4, 2100), 5), 0.0, None, None),    # rows span 17 pieces, TMA path
     "noise_long_rows_odd": (lambda: inputs.noise((3, 4, 2101), 5), 0.0, None, None),  # same, generic loader
     "noise_long_rows_flat": (lambda: inputs.noise((2, 3, 2048), 6), 0.0, None, None),
+    # rows of 17..128 bit words: the row-streaming face pass (mc_faces_rows.cu), 1 / 2 / 4 words per lane
+    "noise_rows_np8": (lambda: inputs.noise((6, 7, 1024), 20), 0.0, None, None),
+    "noise_rows_np6": (lambda: inputs.noise((5, 9, 700), 21), 0.0, None, None),
+    "noise_rows_np5_odd": (lambda: inputs.noise((4, 5, 611), 22), 0.0, None, None),
+    "noise_rows_np12": (lambda: inputs.noise((3, 5, 1500), 23), 0.0, None, None),
+    "noise_rows_np32": (lambda: inputs.noise((3, 3, 4096), 24), 0.0, None, None),
+    "waves_rows_np8": (lambda: inputs.waves((40, 150, 1000)), 0.0, None, None),
+    "waves_rows_np16": (lambda: inputs.waves((10, 70, 2048)), 0.1, None, None),
     "noise_piece_edges": (lambda: inputs.noise((10, 11, 257), 15), 0.0, None, None),  # piece boundary at 128, 256
     "noise_blocks": (lambda: inputs.noise((17, 25, 132), 16), 0.0, None, None),      # partial x/y blocks
     "noise_dense_tile": (lambda: inputs.noise((9, 9, 384), 17), 0.0, None, None),    # > 2048 vertices per tile
@@ -365,11 +374,19 @@ def test_gyroid_generator_is_bit_identical_on_gpu():
     assert np.array_equal(_gyroid_cuda(64).cpu().numpy().view(np.uint32), inputs.gyroid(64).view(np.uint32))
 
 
-def test_gyroid1024_full_size_properties():
-    """BASELINE config 3 at full size (the oracle does not run here): known-answer counts and
-    size-independent properties -- every index valid and used, every vertex on exactly one grid
-    edge, each triangle inside one cell, and a slab of the result equal to the oracle's
-    extraction of the same planes."""
+def _sorted_rows_u32(rows):
+    """[N, C] int64 keys (32 bits each) sorted lexicographically, on the GPU (stable sorts, last column first)."""
+    order = torch.arange(rows.shape[0], device=rows.device)
+    for c in range(rows.shape[1] - 1, -1, -1):
+        order = order[torch.sort(rows[order, c], stable=True).indices]
+    return rows[order]
+
+
+def test_gyroid1024_full_size_against_the_oracle():
+    """BASELINE config 3 at FULL size against the 64-bit oracle: known-answer counts, the vertex multiset bit for
+    bit, and every triangle (9 corner coordinates, emitted corner order) in the oracle's order -- both sides emit
+    faces voxel-major (marching_cubes.cu:194-208), so no sorting is involved.  Plus the size-independent properties:
+    every index used, every vertex on exactly one grid edge, every triangle inside one cell."""
     from primitive3d_b200 import capi
     n = 1024
     g = _gyroid_cuda(n)
@@ -377,33 +394,29 @@ def test_gyroid1024_full_size_properties():
     V, F, ws, vbuf = capi.mc_count(desc, g)
     assert (V, F) == (40621056, 81103132)
     verts, faces = capi.mc_vertices(desc, g, ws, V, vbuf), capi.mc_faces(desc, ws, F)
-    del vbuf
+    del vbuf, ws
     assert int(faces.min()) == 0 and int(faces.max()) == V - 1
     used = torch.zeros(V, dtype=torch.bool, device="cuda")
     used[faces.reshape(-1).long()] = True
     assert bool(used.all())
     frac = verts - torch.floor(verts)
     assert int(((frac != 0).sum(1) > 1).sum()) == 0
-    tri = verts[faces.reshape(-1).long()].reshape(-1, 3, 3)
-    ext = tri.max(1).values - tri.min(1).values
-    assert float(ext.max()) <= 1.0
-    # faces are voxel-major: the owning cell's linear index never decreases
-    cell = torch.floor(tri.min(1).values).long()
-    lin = (cell[:, 0] * n + cell[:, 1]) * n + cell[:, 2]
-    assert bool((lin[1:] >= lin[:-1]).all())
-    del used, frac, ext, cell, lin
-    # slab check against the oracle: planes [500, 508) as a stand-alone grid
-    sub = g[500:509].contiguous()
-    ov, of = mc.marching_cubes(sub.cpu().numpy(), 0.0, [0, 0, 0], [9, n, n])
-    keep = (tri[:, :, 0].min(1).values >= 500) & (tri[:, :, 0].max(1).values <= 508) & \
-           (torch.floor(tri[:, :, 0].min(1).values) < 508)
-    ours = tri[keep].clone()
-    ours[:, :, 0] -= 500
-    want = torch.from_numpy(ov)[torch.from_numpy(of).long().reshape(-1)].reshape(-1, 3, 3)
-    # the sub-grid's last plane owns no cells, so its cell set is x in [0, 8): same triangles
-    assert ours.shape == want.shape
-    ours = ours.cpu()
-    # y and z are bit-identical; x was rounded at magnitude ~500 (float(x) + dt, marching_cubes.cu:107)
-    # on our side and at magnitude ~1 in the stand-alone slab, so it agrees to one ulp of 512
-    assert torch.equal(ours[:, :, 1:], want[:, :, 1:])
-    assert float((ours[:, :, 0] - want[:, :, 0]).abs().max()) <= 2.0 ** -14
+    del used, frac
+    # the oracle on the same grid (OpenMP, 64-bit indices: a few seconds)
+    ov, of = mc.marching_cubes(g.cpu().numpy(), 0.0)
+    del g
+    assert ov.shape == (V, 3) and of.shape == (F, 3)
+    ov, of = torch.from_numpy(ov).cuda(), torch.from_numpy(of).cuda()
+    # triangles, in order: corner coordinates as raw bits, chunked to bound the temporaries
+    step = 1 << 23
+    for a in range(0, F, step):
+        ours = verts[faces[a:a + step].reshape(-1).long()].view(torch.int32)
+        want = ov[of[a:a + step].reshape(-1).long()].view(torch.int32)
+        assert torch.equal(ours, want), f"triangles [{a}, {a + step}) differ from the oracle's"
+        tri = verts[faces[a:a + step].reshape(-1).long()].reshape(-1, 3, 3)
+        assert float((tri.max(1).values - tri.min(1).values).max()) <= 1.0
+    del ours, want, tri
+    # vertex multisets, bit for bit
+    mine = _sorted_rows_u32(verts.view(torch.int32).long() & 0xffffffff)
+    theirs = _sorted_rows_u32(ov.view(torch.int32).long() & 0xffffffff)
+    assert torch.equal(mine, theirs)

@@ -37,7 +37,7 @@ def test_capi_matches_reference_golden(name):
     assert (e[:, 0] < e[:, 1]).all()
 
 
-@pytest.mark.parametrize("n", [32, 64])
+@pytest.mark.parametrize("n", [32, 64, 128])  # 128 = BASELINE configs[3]
 def test_kuhn_grid_matches_oracle(n):
     pts, tets, sdf = inputs.kuhn_tet_grid(n)
     v, f, ti, e, tets_after = run_capi(pts, tets, sdf)
@@ -45,6 +45,8 @@ def test_kuhn_grid_matches_oracle(n):
     ov, of, oti = mt.marching_tetrahedras(pts, o_tets, sdf, True)
     if n == 32:
         assert (len(ov), len(of)) == (3314, 6624)
+    if n == 128:
+        assert (len(ov), len(of)) == (56786, 113568)
     assert np.array_equal(tets_after, o_tets)
     assert np.array_equal(v.view(np.uint32), ov.view(np.uint32))
     assert np.array_equal(f, of) and np.array_equal(ti, oti)
@@ -124,15 +126,16 @@ def test_gradients_match_torch_autograd_of_the_reference_formula():
     assert torch.allclose(gs, s2.grad, rtol=1e-3, atol=1e-3 * float(s2.grad.abs().max()))
 
 
-def test_against_reference_module_on_gpu():
+@pytest.mark.parametrize("n", [48, 128])  # 128 = BASELINE configs[3]
+def test_against_reference_module_on_gpu(n):
     """The reference's own torch implementation run on the same GPU (staged copy in oracle/_ref)."""
     path = os.path.join(ROOT, "oracle", "_ref", "ref_marching_tetrahedras.py")
-    if not os.path.exists(path):
-        pytest.skip("oracle/_ref/ref_marching_tetrahedras.py not staged")
+    # a missing staged reference is a FAILURE of the GPU suite, not a skip
+    assert os.path.exists(path), "oracle/_ref/ref_marching_tetrahedras.py is not staged (python oracle/build_ref.py)"
     spec = importlib.util.spec_from_file_location("ref_mt", path)
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
-    pts, tets, sdf = inputs.kuhn_tet_grid(48)
+    pts, tets, sdf = inputs.kuhn_tet_grid(n)
     margin = mt.orientation_margin(pts, tets)
     assert margin.min() > 1e-6   # no numerically degenerate tets, torch.det's sign is reliable
     P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sdf).cuda()

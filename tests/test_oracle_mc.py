@@ -16,18 +16,34 @@ def bunny():
     return np.load(os.path.join(HERE, "golden", "mc_bunny66.npz"))["grid"]
 
 
+def bunny256():
+    """BASELINE configs[1]: the bunny grid at 256^3."""
+    return inputs.upsample_trilinear(bunny(), 256)
+
+
 KNOWN = [  # (name, grid factory, V, F)  -- SURVEY.md Appendix B
     ("sphere200", lambda: inputs.sphere_int64(200).astype(np.float32), 11766, 23528),
     ("sphere128", lambda: inputs.sphere_int64(128).astype(np.float32), 11766, 23528),
     ("bunny66", bunny, 13282, 26560),
     ("gyroid128", lambda: inputs.gyroid(128), 635904, 1261852),
     ("gyroid256", lambda: inputs.gyroid(256), 2500608, 4972828),
+    ("bunny256", bunny256, 204670, 409336),  # frozen from the oracle (pinned to the compiled reference on the GPU box)
 ]
 
 
 @pytest.mark.parametrize("name,make,V,F", KNOWN, ids=[k[0] for k in KNOWN])
 def test_known_counts(name, make, V, F):
     assert mc.count(make(), 0.0) == (V, F)
+
+
+def test_bunny256_grid_is_reproducible():
+    """The 256^3 bunny is defined by separately rounded fp32 numpy operations: same bits everywhere."""
+    import hashlib
+    g = bunny256()
+    assert g.shape == (256, 256, 256) and g.dtype == np.float32
+    assert hashlib.sha256(g.tobytes()).hexdigest().startswith("fcbb771afab4f064")
+    v, f = mc.marching_cubes(g, 0.0)
+    assert f.shape[0] == 2 * v.shape[0] - 4  # closed, genus 0, like the 66^3 original
 
 
 def test_closed_surface_invariant():
