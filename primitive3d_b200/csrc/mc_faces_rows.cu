@@ -35,6 +35,9 @@
 #ifndef P3D_ROWS_LATE_LOADS
 #define P3D_ROWS_LATE_LOADS 0
 #endif
+#ifndef P3D_ROWS_WARPS
+#define P3D_ROWS_WARPS 8
+#endif
 #ifndef P3D_ROWS_CTAS
 #define P3D_ROWS_CTAS 4  // CTAs per SM of the one-word-per-lane instance (register cap 65536 / (256 * CTAs))
 #endif
@@ -58,7 +61,7 @@ constexpr uint64_t kEdgePair = (0ull << 0) | (10ull << 4) | (4ull << 8) | (8ull 
                                (5ull << 24) | (9ull << 28) | (2ull << 32) | (3ull << 36) | (7ull << 40) | (6ull << 44);
 constexpr int kSlotBytes = 112;    // 12 pairs + 16 bytes: 16-byte stores of eight consecutive slots hit 32 different banks
 
-constexpr int kRowWarps = 8;
+constexpr int kRowWarps = P3D_ROWS_WARPS;
 constexpr int kRowTriCap = 256;    // triangles per window of a row's list
 constexpr int kTaskPieces = 128;   // pieces per chunk of the tile pass's chunk sums
 
@@ -398,6 +401,7 @@ void launch_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, 
     // rows per task: 32 (the first row of a task is read twice), fewer on small grids so that every resident warp
     // gets a few tasks
     int rpt = 32;
+    if (const char *e = getenv("P3D_ROWS_PER_TASK")) rpt = atoi(e) > 0 ? atoi(e) : rpt;  // tuning runs
     const int64_t warps = (int64_t)sm_count() * per_sm * kRowWarps;
     while (rpt > 2 && nrows / rpt < 4 * warps) rpt /= 2;
     const int64_t ntasks = (nrows + rpt - 1) / rpt;

@@ -12,6 +12,16 @@
 #include "mc_case_table.h"
 #include "scan_utils.cuh"
 
+#ifndef P3D_TILE_PIN
+#define P3D_TILE_PIN 0
+#endif
+#ifndef P3D_TILE_QUEUE
+#define P3D_TILE_QUEUE 4
+#endif
+#ifndef P3D_TILE_RING
+#define P3D_TILE_RING 1408
+#endif
+
 
 namespace p3d {
 
@@ -19,6 +29,30 @@ namespace p3d {
 // #triangles).  Lives in constant memory and is staged into shared memory once per
 // persistent CTA because the per-cell lookups are lane-divergent.
 __constant__ uint64_t c_case_table[256] = P3D_MC_CASE_TABLE_INIT;
+
+// Per corner code in staging order a0 a1 b0 b1 c0 c1 d0 d1 (a = (x,y), b = (x+1,y), c = (x+1,y+1), d = (x,y+1); 0 = sample
+// z, 1 = sample z+1): the case's correction  #triangles - (#crossed edges - 2), 0 for the two cases without triangles.
+// Built at compile time from the case table (corner numbering of marching_cubes.cu:50-57, edges of :178-192).
+struct NtriCorrection {
+    int8_t v[256];
+};
+constexpr NtriCorrection make_ntri_correction() {
+    constexpr uint64_t table[256] = P3D_MC_CASE_TABLE_INIT;
+    constexpr int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+    NtriCorrection r{};
+    for (unsigned c = 0; c < 256; ++c) {
+        // staged bit0 = corner 0, bit1 = corner 4, bit2 = corner 1, bit3 = corner 5, bit4 = corner 2, bit5 = corner 6,
+        // bit6 = corner 3, bit7 = corner 7
+        const unsigned cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
+                            ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
+        const int nt = (int)(table[cs] >> 60);
+        int ne = 0;
+        for (int e = 0; e < 12; ++e) ne += (int)(((cs >> ea[e]) ^ (cs >> eb[e])) & 1u);
+        r.v[c] = (int8_t)(ne ? nt - (ne - 2) : 0);
+    }
+    return r;
+}
+__constant__ NtriCorrection c_ntri_correction = make_ntri_correction();
 
 // Bits of word w (32 samples from z = 32*w) with z + 1 < rz: samples that own a +z edge / a cell.
 __device__ __forceinline__ uint32_t low_mask(int64_t n) {
@@ -169,15 +203,26 @@ __device__ __forceinline__ bool scan_prefix(const McScan &sc, uint32_t item, int
 // vertex id (asked for without blocking, one iteration later) -> write vertices (position = integer corner + dt
 // on one axis) and the table entries.  The load of the next tile and the wait for the scan overlap.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRing = 1408;     // pending crossing edges of a CTA (6 bytes each): ~4.5 tiles of the gyroid case
-constexpr int kQueue = 4;       // pending tiles of a CTA
+constexpr int kRing = P3D_TILE_RING;  // pending crossing edges of a CTA (6 bytes each): ~4.5 tiles of the gyroid case
+constexpr int kQueue = P3D_TILE_QUEUE;  // pending tiles of a CTA
 constexpr int kSbitsStride = 8;
 constexpr int kRowPitch = kTileY + 1;  // staged rows per plane
+// position in the ring of entry `pos` (< 2 * kRing): a mask when the ring is a power of two
+__device__ __forceinline__ uint32_t ring_wrap(uint32_t pos) {
+    if ((kRing & (kRing - 1)) == 0) return pos & (uint32_t)(kRing - 1);
+    return pos >= (uint32_t)kRing ? pos - (uint32_t)kRing : pos;
+}
+
+struct TileCoord {          // a tile and where its side products go
+    int x0, y0, p, tile;
+    long long piece_base;   // index of the (row, piece) pair (x0, y0, p) in the per-piece arrays; its bit words start at 4 x that
+    long long pad;
+};
 
 struct PendingTile {
-    int4 coord;            // {x0, y0, piece, tile}
-    uint32_t start, count; // its entries in the ring
-    uint32_t pad[2];
+    int x0, y0, p, tile;
+    uint32_t start, count;  // its entries in the ring
+    long long piece_base;
 };
 
 struct TileSmem {
@@ -194,10 +239,18 @@ struct TileSmem {
     unsigned long long base;       // result of warp 0's non-blocking look-back at the top of an iteration
     unsigned long long base_wait;  // result of a blocking look-back
     uint32_t base_ok;
-    int4 coord[2];         // {x0, y0, piece, tile} of the tile of iteration it, by parity
+    TileCoord coord[2];    // the tile of iteration it, by parity
 };
 constexpr int kTileSmemBytes = kStageBytes + (int)sizeof(TileSmem) + 128;
 static_assert(4 * (kTileSmemBytes + 1024) <= 228 * 1024, "k_tile is tuned for four CTAs per SM");
+
+// (1 << n) - 1 for n in [0, 32]; PTX shl.b32 gives 0 for a shift of 32 (the C++ operator is undefined there)
+__device__ __forceinline__ uint32_t low_mask_clamped(int n) {
+    uint32_t r;
+    const int m = n < 0 ? 0 : (n > 32 ? 32 : n);
+    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(m));
+    return r - 1u;
+}
 
 template <bool TMA, typename T>
 __global__ void __launch_bounds__(kTileThreads, 4)
@@ -214,41 +267,29 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     const float thresh = prm.thresh;
     const int xg0 = (int)prm.x_origin;  // global index of local plane 0 (< 2^31)
 
-    // ntri by staged corner order: bit0 = corner 0 (a, z), bit1 = corner 4 (a, z+1), bit2 = corner 1 (b, z),
-    // bit3 = corner 5, bit4 = corner 2 (c, z), bit5 = corner 6, bit6 = corner 3 (d, z), bit7 = corner 7
-    // (corner numbering of marching_cubes.cu:50-57)
-    {
-        const uint32_t c = tid;
-        const uint32_t cs = (c & 1u) | ((c >> 1 & 1u) << 4) | ((c >> 2 & 1u) << 1) | ((c >> 3 & 1u) << 5) | ((c >> 4 & 1u) << 2) |
-                            ((c >> 5 & 1u) << 6) | ((c >> 6 & 1u) << 3) | ((c >> 7 & 1u) << 7);
-        const int nt = (int)(c_case_table[cs] >> 60);
-        // crossed edges of the case, cube edges in the numbering of marching_cubes.cu:178-192
-        const int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
-        int ne = 0;
-#pragma unroll
-        for (int e = 0; e < 12; ++e) ne += (int)(((cs >> ea[e]) ^ (cs >> eb[e])) & 1u);
-        S.ntri[c] = (int8_t)(ne ? nt - (ne - 2) : 0);
-    }
+    S.ntri[tid] = c_ntri_correction.v[tid];
 
     // Tile id -> coordinates.  Tiles are ordered band by band (a band = `band` y-blocks over all x), inside a
     // band x-block major, then y-block, then piece: the x halo plane of a block is re-read from L2, not HBM.
     auto locate = [&](uint32_t t) {
-        int4 c = make_int4(0, 0, 0, (int)t);
+        TileCoord c;
+        c.x0 = c.y0 = c.p = 0, c.tile = (int)t, c.piece_base = 0, c.pad = 0;
         if (t < ntiles) {
             const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
             const uint32_t bi = t / per_band, rem = t - bi * per_band;
             const uint32_t left = (uint32_t)g.nyb - bi * (uint32_t)g.band, cur = left < (uint32_t)g.band ? left : (uint32_t)g.band;
             const uint32_t xb = rem / (cur * np), rem2 = rem - xb * (cur * np);
             const uint32_t yb = rem2 / np, p = rem2 - yb * np;
-            c.x = (int)(xb * kTileX), c.y = (int)((bi * g.band + yb) * kTileY), c.z = (int)p;
+            c.x0 = (int)(xb * kTileX), c.y0 = (int)((bi * g.band + yb) * kTileY), c.p = (int)p;
+            c.piece_base = ((long long)c.x0 * ry + c.y0) * np + c.p;
         }
         return c;
     };
-    auto issue = [&](const int4 &c) {  // one thread, once the stage is free
-        if (TMA && (uint32_t)c.w < ntiles) {
+    auto issue = [&](const TileCoord &c) {  // one thread, once the stage is free
+        if (TMA && (uint32_t)c.tile < ntiles) {
             const uint32_t bar = smem_u32(&S.bar);
             mbar_expect_tx(bar, kBoxRows * kBoxZ * 4);
-            tma_load_3d(smem_u32(tf), &tmap, bar, c.z * kTileZ, c.y, c.x);
+            tma_load_3d(smem_u32(tf), &tmap, bar, c.p * kTileZ, c.y0, c.x0);
         }
     };
     if (tid == 0) {
@@ -256,7 +297,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             mbar_init(smem_u32(&S.bar), 1);
             mbar_fence_init();
         }
-        const int4 c = locate(atomicAdd(&ws.header->ticket, 1u));
+        const TileCoord c = locate(atomicAdd(&ws.header->ticket, 1u));
         S.coord[0] = c;
         issue(c);
     }
@@ -265,8 +306,16 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     // my word of the tile (count phase): row r = (xi, yi), word w
     const int r = tid >> 2, w = tid & 3;
     const int xi = r >> 3, yi = r & 7;
-    const uint32_t *sa = &S.sbits[(xi * kRowPitch + yi) * kSbitsStride + w];
-    const int64_t bstride = 4 * (int64_t)np;  // bit words per row
+    int sa_index = (xi * kRowPitch + yi) * kSbitsStride + w;
+    // my (row, piece) pair relative to the tile's first, in the per-piece arrays
+    long long my_piece_off = ((long long)xi * ry + yi) * np;
+    int zlim = rz - 1 - 32 * w;  // samples of my word with z + 1 < rz: zlim - z0 of them
+#if P3D_TILE_PIN
+    // per-thread constants of the tile loop: opaque to the compiler, which otherwise recomputes them from threadIdx
+    // for every tile to stay under a register count it does not need to stay under
+    asm volatile("" : "+r"(sa_index), "+l"(my_piece_off), "+r"(zlim));
+#endif
+    const uint32_t *sa = &S.sbits[sa_index];
 
     // one crossing edge -> its vertex (gen_vertices_kernel :70-138 and the epilogue :298)
     auto edge_dt = [&](uint32_t ent) {
@@ -277,16 +326,13 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // dt = (thresh - d_self) / (d_next - d_self), IEEE fp32, no contraction (:105)
         return __fdiv_rn(__fsub_rn(thresh, d0), __fsub_rn(d1, d0));
     };
-    auto put_vertex = [&](unsigned long long id, uint32_t ent, float dt, int x0, int y0, int z0) {
-        const uint32_t ax = ent >> 13, er = (ent >> 7) & 63u, ez = ent & 127u;
-        float px = (float)(xg0 + x0 + (int)(er >> 3));  // static_cast<float>(x), :107
-        float py = (float)(y0 + (int)(er & 7u));
-        float pz = (float)(z0 + (int)ez);
-        if (ax == 0) px = __fadd_rn(px, dt);
-        if (ax == 1) py = __fadd_rn(py, dt);
-        if (ax == 2) pz = __fadd_rn(pz, dt);
-        // vertices * scale + offset as two separately rounded ops (:298)
-        float *out = verts + id * 3ull;
+    // position = float(voxel) + dt on the edge's axis (:107; adding +0.0f to the other two changes nothing: they are
+    // >= 0), then vertices * scale + offset as two separately rounded ops (:298)
+    auto put_vertex = [&](float *out, uint32_t ent, float dt, int x0g, int y0, int z0) {
+        const uint32_t ax = ent >> 13;
+        const float px = __fadd_rn((float)(x0g + (int)((ent >> 10) & 7u)), ax == 0 ? dt : 0.0f);
+        const float py = __fadd_rn((float)(y0 + (int)((ent >> 7) & 7u)), ax == 1 ? dt : 0.0f);
+        const float pz = __fadd_rn((float)(z0 + (int)(ent & 127u)), ax == 2 ? dt : 0.0f);
         out[0] = __fadd_rn(__fmul_rn(px, prm.scale[0]), prm.offset[0]);
         out[1] = __fadd_rn(__fmul_rn(py, prm.scale[1]), prm.offset[1]);
         out[2] = __fadd_rn(__fmul_rn(pz, prm.scale[2]), prm.offset[2]);
@@ -302,26 +348,36 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     // The table entries of a tile {first x-/y-/z-edge vertex id, triangle count} per (row, piece) are known relative
     // to the tile in the count phase; they wait in shared memory with the tile's vertices and are written once,
     // absolute, when the tile's first vertex id is known: the face pass needs no per-tile indirection and the
-    // table is never read back.  Thread 4 * row writes the entry of its row.
-    auto write_entry = [&](const int4 &c, uint2 rel, unsigned long long base, uint32_t count) {
-        if (mode == 0 && (tid & 3) == 0) {
-            const int tx = c.x + (tid >> 5), ty = c.y + ((tid >> 2) & 7);
-            if (tx < ox && ty < ry)
-                ws.ptab[((int64_t)tx * ry + ty) * np + c.z] =
-                    make_uint4((rel.x & 0xffffu) + (uint32_t)base, (rel.x >> 16) + (uint32_t)base, (rel.y & 0xffffu) + (uint32_t)base, rel.y >> 16);
+    // table is never read back.  Thread `row` (< 64) writes the entry of row `row`.
+    auto write_entries = [&](int x0, int y0, long long piece_base, uint32_t tile, const uint2 *rel, unsigned long long base,
+                             uint32_t count) {
+        if (mode == 0 && tid < kTileX * kTileY) {
+            const int ex = tid >> 3, ey = tid & 7;
+            if (x0 + ex < ox && y0 + ey < ry) {
+                const uint2 e = rel[tid];
+                ws.ptab[piece_base + ((long long)ex * ry + ey) * np] =
+                    make_uint4((e.x & 0xffffu) + (uint32_t)base, (e.x >> 16) + (uint32_t)base, (e.y & 0xffffu) + (uint32_t)base, e.y >> 16);
+            }
         }
-        if (mode == 0 && tid == 0 && (uint32_t)c.w == ntiles - 1) ws.header->total_v = base + count;
+        if (mode == 0 && tid == 0 && tile == ntiles - 1) ws.header->total_v = base + count;
     };
     // vertices of the pending tile in queue slot `slot`, whose first vertex id is `base`
     auto retire = [&](uint32_t slot, unsigned long long base) {
-        const int4 c = S.q[slot].coord;
-        const uint32_t start = S.q[slot].start, count = S.q[slot].count;
-        write_entry(c, S.prel[slot][tid >> 2], base, count);
-        for (uint32_t k = tid; k < count; k += kTileThreads) {
-            uint32_t idx = start + k;
-            if (idx >= (uint32_t)kRing) idx -= kRing;
-            const unsigned long long id = base + k;
-            if (id < vcap) put_vertex(id, S.ent[idx], S.dt[idx], c.x, c.y, c.z * kTileZ);
+        const PendingTile &q = S.q[slot];
+        const uint32_t start = q.start, count = q.count;
+        const int x0g = xg0 + q.x0, y0 = q.y0, z0 = q.p * kTileZ;
+        write_entries(q.x0, y0, q.piece_base, (uint32_t)q.tile, S.prel[slot], base, count);
+        float *const out0 = verts + base * 3ull;
+        if (base + count <= vcap) {
+            for (uint32_t k = tid; k < count; k += kTileThreads) {
+                const uint32_t idx = ring_wrap(start + k);
+                put_vertex(out0 + 3u * k, S.ent[idx], S.dt[idx], x0g, y0, z0);
+            }
+        } else {  // the speculative buffer ends inside this tile
+            for (uint32_t k = tid; k < count; k += kTileThreads) {
+                const uint32_t idx = ring_wrap(start + k);
+                if (base + k < vcap) put_vertex(out0 + 3u * k, S.ent[idx], S.dt[idx], x0g, y0, z0);
+            }
         }
         ring_used -= count;
         q_head = (q_head + 1) % kQueue;
@@ -341,10 +397,11 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     };
 
     for (uint32_t it = 0;; ++it) {
-        const int4 tc = S.coord[it & 1u];
-        const uint32_t tile = (uint32_t)tc.w;
+        const TileCoord &tc = S.coord[it & 1u];
+        const uint32_t tile = (uint32_t)tc.tile;
         if (tile >= ntiles) break;
-        const int x0 = tc.x, y0 = tc.y, p = tc.z, z0 = p * kTileZ;
+        const int x0 = tc.x0, y0 = tc.y0, p = tc.p, z0 = p * kTileZ;
+        const long long piece_base = tc.piece_base;
 
         // ticket of this CTA's next tile, asked for a whole tile ahead of its use.  Tiles are handed out in
         // increasing order to running CTAs: every tile before a tile is finished or in flight, whatever the
@@ -356,7 +413,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // trip to L2 hides behind the TMA wait.  Non-blocking.
         if (q_count && warp == 0) {
             unsigned long long tb = 0;
-            const bool ok = scan_prefix<false>(ws.vscan, (uint32_t)S.q[q_head].coord.w, lane, tb);
+            const bool ok = scan_prefix<false>(ws.vscan, (uint32_t)S.q[q_head].tile, lane, tb);
             if (lane == 0) {
                 S.base_ok = ok ? 1u : 0u;
                 S.base = tb;
@@ -407,7 +464,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t D = sa[kSbitsStride], Dn = sa[kSbitsStride + 1];
         const uint32_t C = sa[(kRowPitch + 1) * kSbitsStride], Cn = sa[(kRowPitch + 1) * kSbitsStride + 1];
         const uint32_t A2 = __funnelshift_r(A, An, 1);
-        const uint32_t zv = low_mask(rz - 1 - (z0 + 32 * w));  // samples with z + 1 < rz
+        const uint32_t zv = low_mask_clamped(zlim - z0);  // samples with z + 1 < rz
         const uint32_t m0 = hx ? (A ^ B) : 0u;            // +x edges, :29-33 / :100-111
         const uint32_t m1 = hy ? (A ^ D) : 0u;            // +y edges, :35-39 / :113-124
         const uint32_t m2 = own ? ((A ^ A2) & zv) : 0u;   // +z edges, :41-45 / :126-137
@@ -443,7 +500,8 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             nf = (uint32_t)total;
         }
         // my (row, piece) = 4 adjacent lanes: packed {nx, ny, nz} (8-bit fields, <= 128 each)
-        const uint32_t cnt = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 8) | ((uint32_t)__popc(m2) << 16);
+        const uint32_t cx = (uint32_t)__popc(m0), cy = (uint32_t)__popc(m1), cz = (uint32_t)__popc(m2);
+        const uint32_t cnt = cx | (cy << 8) | (cz << 16);
         uint32_t inc = cnt;
         {
             uint32_t t = __shfl_up_sync(kFull, inc, 1);
@@ -459,17 +517,17 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         nfw += __shfl_xor_sync(kFull, nfw, 2);
         nf = __dp4a(nfw, 0x01010101u, 0u);  // of the piece
         if (w == 0) {
-            S.piece[r] = (tot & 255u) + ((tot >> 8) & 255u) + (tot >> 16);
+            S.piece[r] = __dp4a(tot, 0x01010101u, 0u);
             S.nfp[r] = (uint16_t)nf;  // <= 640
         }
 
-        const int64_t grow = (int64_t)x * ry + y;  // my row of the grid
         if (mode == 0) {
-            if (x < rx && y < ry) ws.bits[grow * bstride + 4 * p + w] = A;
-            if (own && w == 0) ws.nf[grow * np + p] = nfw;
+            const long long mine = piece_base + my_piece_off;  // my (row, piece) in the per-piece arrays
+            if (x < rx && y < ry) ws.bits[4 * mine + w] = A;
+            if (own && w == 0) ws.nf[mine] = nfw;
             // the halo plane of a slab sits one past the last x-block when owned_x is a multiple of 8
             if (tid < 32 && x0 + kTileX == ox && ox < rx && y0 + (tid >> 2) < ry)
-                ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * bstride + 4 * p + (tid & 3)] =
+                ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * (4 * (int64_t)np) + 4 * p + (tid & 3)] =
                     S.sbits[(kTileX * kRowPitch + (tid >> 2)) * kSbitsStride + (tid & 3)];
         }
         // the look-back result of the top of this iteration: written by warp 0 before [bits], read here, and not
@@ -494,7 +552,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             wcount = __shfl_sync(kFull, seg, 4 * warp);
         }
         // face offsets of the face pass: triangle counts summed per chunk of 128 consecutive (row, piece) pairs.
-        // Warp 0, a lane per x-row of the tile (its 8 rows are one RED when they fall into one chunk).
+        // Warp 7, a lane per x-row of the tile (its 8 rows are one RED when they fall into one chunk).
         if (mode == 0 && warp == 7) {
             const uint32_t v2 = *reinterpret_cast<const uint32_t *>(&S.nfp[2 * lane]);
             uint32_t t = (v2 & 0xffffu) + (v2 >> 16);
@@ -508,7 +566,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             if ((lane & 3) == 0 && t) {
                 constexpr int64_t kChunkPieces = kFacePieces * kFaceChunk;
                 const int xr = lane >> 2, ylast = (y0 + kTileY <= ry ? y0 + kTileY : ry) - 1;
-                const int64_t gfirst = ((int64_t)(x0 + xr) * ry + y0) * np + p, glast = ((int64_t)(x0 + xr) * ry + ylast) * np + p;
+                const int64_t gfirst = piece_base + (int64_t)xr * ry * np, glast = gfirst + (int64_t)(ylast - y0) * np;
                 if (gfirst / kChunkPieces == glast / kChunkPieces) {
                     atomicAdd(ws.chunk_sum + gfirst / kChunkPieces, t);
                 } else {
@@ -525,66 +583,72 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         const uint32_t vx_rel = pe, vy_rel = pe + (tot & 255u), vz_rel = vy_rel + ((tot >> 8) & 255u);
         // table entry of my (row, piece), relative to the tile (every field < 2^16: a tile has <= 24576 vertices)
         const uint2 my_entry = make_uint2(vx_rel | (vy_rel << 16), vz_rel | (nf << 16));
-        const uint32_t first[3] = {vx_rel + (exw & 255u), vy_rel + ((exw >> 8) & 255u), vz_rel + (exw >> 16)};
+        // one past the last entry of my word's crossings, per axis (relative to the tile)
+        const uint32_t last[3] = {vx_rel + (exw & 255u) + cx, vy_rel + ((exw >> 8) & 255u) + cy, vz_rel + (exw >> 16) + cz};
         const uint32_t wmask[3] = {m0, m1, m2};
         const uint32_t ecode = (uint32_t)((r << 7) | (w << 5));
         if (vt <= (uint32_t)kRing) {
             // ---- make room in the ring (rare): retire the oldest pending tiles, waiting for their ids ----
             while (q_count && (ring_used + vt > (uint32_t)kRing || q_count == (uint32_t)kQueue)) {
                 unsigned long long tb = probe_base;
-                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].coord.w);
+                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].tile);
                 probe_ok = false;
                 retire(q_head, tb);
                 __syncthreads();  // its entries may be overwritten now
             }
-            // ---- my crossing edges -> ring; my warp interpolates its own (contiguous) range ----
+            // ---- my crossing edges -> ring (last to first); my warp interpolates its own (contiguous) range ----
             const uint32_t start = ring_tail;
             if (w == 0) S.prel[(q_head + q_count) % kQueue][r] = my_entry;
 #pragma unroll
             for (int ax = 0; ax < 3; ++ax) {
-                uint32_t pos = start + first[ax];
-                if (pos >= (uint32_t)kRing) pos -= kRing;
+                uint32_t pos = start + last[ax];
+                const uint32_t code = (uint32_t)(ax << 13) | ecode;
                 for (uint32_t rem = wmask[ax]; rem;) {
-                    const int i = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    S.ent[pos] = (uint16_t)((ax << 13) | ecode | i);
-                    if (++pos == (uint32_t)kRing) pos = 0;
+                    const int i = 31 - __clz(rem);
+                    rem ^= 1u << i;
+                    --pos;
+                    S.ent[ring_wrap(pos)] = (uint16_t)(code | i);
                 }
             }
             __syncwarp();
             for (uint32_t k = lane; k < wcount; k += 32) {
-                uint32_t idx = start + wbase + k;
-                if (idx >= (uint32_t)kRing) idx -= kRing;
+                const uint32_t idx = ring_wrap(start + wbase + k);
                 S.dt[idx] = edge_dt(S.ent[idx]);
             }
             if (tid == 0) {
                 PendingTile &q = S.q[(q_head + q_count) % kQueue];
-                q.coord = tc;
+                q.x0 = x0, q.y0 = y0, q.p = p, q.tile = (int)tile;
                 q.start = start;
                 q.count = vt;
+                q.piece_base = piece_base;
             }
             ++q_count;
             ring_used += vt;
-            ring_tail = start + vt >= (uint32_t)kRing ? start + vt - kRing : start + vt;
+            ring_tail = ring_wrap(start + vt);
         } else {
             // ---- more crossings than the ring holds (noise-like data): retire everything pending, wait for
             // this tile's first id, and emit it chunk by chunk from the stage ----
             while (q_count) {
                 unsigned long long tb = probe_base;
-                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].coord.w);
+                if (!probe_ok) tb = wait_base((uint32_t)S.q[q_head].tile);
                 probe_ok = false;
                 retire(q_head, tb);
             }
             const unsigned long long tb = wait_base(tile);
-            write_entry(tc, my_entry, tb, vt);  // thread 4 * row holds the entry of its row
+            // the entries go through the (idle) first queue slot: thread `row` writes the entry of row `row`
+            if (w == 0) S.prel[0][r] = my_entry;
+            __syncthreads();
+            write_entries(x0, y0, piece_base, tile, S.prel[0], tb, vt);
             for (uint32_t c0 = 0; c0 < vt; c0 += kRing) {
 #pragma unroll
                 for (int ax = 0; ax < 3; ++ax) {
-                    uint32_t pos = first[ax] - c0;  // wraps for entries below the chunk: filtered by the range test
-                    for (uint32_t rem = wmask[ax]; rem; ++pos) {
-                        const int i = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        if (pos < (uint32_t)kRing) S.ent[pos] = (uint16_t)((ax << 13) | ecode | i);
+                    uint32_t pos = last[ax] - c0;  // wraps for entries outside the chunk: filtered by the range test
+                    const uint32_t code = (uint32_t)(ax << 13) | ecode;
+                    for (uint32_t rem = wmask[ax]; rem;) {
+                        const int i = 31 - __clz(rem);
+                        rem ^= 1u << i;
+                        --pos;
+                        if (pos < (uint32_t)kRing) S.ent[pos] = (uint16_t)(code | i);
                     }
                 }
                 __syncthreads();
@@ -592,26 +656,22 @@ __global__ void __launch_bounds__(kTileThreads, 4)
                 for (uint32_t k = tid; k < n; k += kTileThreads) {
                     const unsigned long long id = tb + c0 + k;
                     const uint32_t ent = S.ent[k];
-                    if (id < vcap) put_vertex(id, ent, edge_dt(ent), x0, y0, z0);
+                    if (id < vcap) put_vertex(verts + id * 3ull, ent, edge_dt(ent), xg0 + x0, y0, z0);
                 }
                 __syncthreads();
             }
             ring_tail = 0;
         }
         // the next tile's coordinates are published before the barrier, its load is issued after it
-        int4 nc = make_int4(0, 0, 0, 0);
-        if (tid == 32) {
-            nc = locate(next_tile);
-            S.coord[(it + 1u) & 1u] = nc;
-        }
+        if (tid == 32) S.coord[(it + 1u) & 1u] = locate(next_tile);
         __syncthreads();  // [stage free]
-        if (tid == 32) issue(nc);
+        if (tid == 32) issue(S.coord[(it + 1u) & 1u]);
 
         // ---- the oldest pending tile, if the look-back at the top of this iteration found its first id ----
         if (probe_ok) retire(q_head, probe_base);
     }
     while (q_count) {  // the tiles still pending
-        const unsigned long long tb = wait_base((uint32_t)S.q[q_head].coord.w);
+        const unsigned long long tb = wait_base((uint32_t)S.q[q_head].tile);
         retire(q_head, tb);
     }
 }
