@@ -393,10 +393,13 @@ template <int NW>
 void launch_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
                  bool vertex_base_from_header, cudaStream_t s) {
     constexpr int smem = 512 * (int)sizeof(uint2) + kRowWarps * (int)sizeof(RowScratch<NW>);
-    cudaFuncSetAttribute(k_faces_rows<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_faces_rows<NW>, kRowWarps * 32, smem);
-    if (per_sm < 1) per_sm = 1;
+    static int cache[kMaxDevices];
+    const int per_sm = per_device(cache, [] {
+        cudaFuncSetAttribute(k_faces_rows<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_faces_rows<NW>, kRowWarps * 32, smem);
+        return n > 0 ? n : 1;
+    });
     const int64_t nrows = g.owned_x * g.ry;
     // rows per task: 32 (the first row of a task is read twice), fewer on small grids so that every resident warp
     // gets a few tasks

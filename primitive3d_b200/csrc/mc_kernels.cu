@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kTileThreads, 4)
         // E summed over the word is twelve popcounts; L = 1 unless the inside or the outside corners fall apart,
         // which needs an ambiguous face (all four edges of a face crossed) or two isolated opposite corners:
         // only those cells are looked up, for their correction  #triangles - (E - 2).
-        if (hc) {                                         // cells :48-66; bit i = cell at sample z0 + 32 w + i
+        if (hc && mode == 0) {                            // cells :48-66; bit i = cell at sample z0 + 32 w + i
             const uint32_t B2 = __funnelshift_r(B, Bn, 1), C2 = __funnelshift_r(C, Cn, 1), D2 = __funnelshift_r(D, Dn, 1);
             const uint32_t xa0 = (A ^ B) & zv, xa1 = (A2 ^ B2) & zv, xd0 = (D ^ C) & zv, xd1 = (D2 ^ C2) & zv;  // x edges
             const uint32_t ya0 = (A ^ D) & zv, ya1 = (A2 ^ D2) & zv, yb0 = (B ^ C) & zv, yb1 = (B2 ^ C2) & zv;  // y edges
@@ -1064,17 +1064,14 @@ bool force_generic() {
 template <bool TMA, typename T>
 void launch_tile_kernel(const CUtensorMap &map, const void *grid, const McGeom &g, const McWorkspace &ws,
                         const McEmitParams &p, float *verts, int64_t vcap, int mode, cudaStream_t s) {
-    static const bool attr = [] {
-        cudaFuncSetAttribute(k_tile<TMA, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
-        return true;
-    }();
-    (void)attr;
     // every CTA must be resident: a CTA waits for tiles with lower ids, which running CTAs hold
-    static const int per_sm = [] {
+    static int cache[kMaxDevices];
+    const int per_sm = per_device(cache, [] {
+        cudaFuncSetAttribute(k_tile<TMA, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
         int n = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA, T>, kTileThreads, kTileSmemBytes);
         return n > 0 ? n : 1;
-    }();
+    });
     const int64_t cap = (int64_t)sm_count() * per_sm;
     const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
     k_tile<TMA, T><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, static_cast<const T *>(grid), g, ws, p, verts,
@@ -1159,11 +1156,11 @@ void launch_faces(const McGeom &g, const McWorkspace &ws, const McEmitParams &p,
     int gpt = kFaceChunk;
     while (gpt > 1 && groups / gpt < 2 * cap * kFaceWarps) gpt /= 2;
     const int64_t want = ((groups + gpt - 1) / gpt + kFaceWarps - 1) / kFaceWarps;
-    static const bool attr = [] {
+    static int cache[kMaxDevices];
+    per_device(cache, [] {
         cudaFuncSetAttribute(k_faces, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaceSmemBytes);
-        return true;
-    }();
-    (void)attr;
+        return 1;
+    });
     k_faces<<<(unsigned)(want < cap ? want : cap), kFaceWarps * 32, kFaceSmemBytes, s>>>(g, ws, p.vertex_id_base, faces,
                                                                                          (unsigned long long)face_capacity,
                                                                                          vertex_base_from_header ? 1 : 0, gpt,

@@ -76,6 +76,19 @@ __device__ __forceinline__ unsigned long long lookback(volatile unsigned long lo
     return excl;
 }
 
+// Function attributes (the opt-in shared-memory size) and occupancy are per DEVICE: a process that uses two GPUs must
+// set them on both.  `setup` runs once per device and returns a positive value (e.g. resident CTAs per SM) that is
+// cached; a host thread that races another one merely repeats the setup.
+constexpr int kMaxDevices = 64;
+template <typename Setup>
+inline int per_device(int (&cache)[kMaxDevices], Setup setup) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return setup();
+    if (cache[dev] == 0) cache[dev] = setup();
+    return cache[dev];
+}
+
 inline int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
