@@ -43,12 +43,12 @@ KNOWN = {1024: (40621056, 81103132), 2048: (162441216, 324595996), 512: (1011148
 
 
 def ncu_traffic(kernel, n):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
-    (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_report.py); None if there is none."""
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this rank's slab (n = its dim-0
+    planes, halo included; profiles/ncu_traffic.json, written from the .ncu-rep files); None if there is none."""
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
-        if rec.get("grid") == n:
-            return rec["dram_bytes_read"] + rec["dram_bytes_write"]
+        for rec in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]:
+            if rec.get("planes") == n:
+                return rec["dram_bytes_read"] + rec["dram_bytes_write"]
     except Exception:
         pass
     return None
@@ -152,11 +152,13 @@ def run_reference_arm(args):
     ms = 1e3 * sum(times) / len(times)
     value = g.size / (ms * 1e-3) / 1e9
     sample = f"planes [0,{planes}) of gyroid {n}^3 ({g.size / 1e6:.0f} Mvoxel) per step"
+    fraction = planes / n   # of the grid named in `config`: the line is a RATE measured on that part
     line = {"impl": "reference", "metric": "marching_cubes_throughput", "value": value, "unit": "Gvoxel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(n, args.gpus),
+            "config": workload_config(n, args.gpus), "sample_fraction": fraction,
             "cpu_baseline": {"value": value, "unit": "Gvoxel/s", "cores": threads, "kind": "port", "sample": sample,
+                             "sample_fraction": fraction,
                              "what": "oracle/mc_oracle.c: OpenMP restatement of marching_cubes.cu (the reference has "
                                      "no CPU implementation of its own; its cpu=True mode calls PyMCubes)"},
             "e2e": {"value": value, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,7 +214,7 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     torch.cuda.synchronize()
 
-    # our kernels per step: k_tile, k_round_sums, k_faces (+ k_export_exchange, k_apply_exchange on several GPUs)
+    # our kernels per step: k_tile, k_round_sums, k_faces_rows (+ k_export_exchange, k_apply_exchange on several GPUs)
     launches_per_step = 3 if world == 1 else 5
 
     if world == 1:
@@ -308,6 +310,44 @@ def main():
                                                        "faces: upload, extraction and download one after the other"}
         del host, hv, hf
 
+    # ---- several GPUs: the same workload on ONE GPU in the same job (rank 0): the base of the strong-scaling factor,
+    # and numbering-independent checksums of the sharded mesh against those of the single-GPU mesh ----
+    verification = strong = None
+    if world > 1 and not args.no_extras:
+        from primitive3d_b200 import verify
+        out = step()
+        sums = verify.mesh_checksums(out.vertices, out.faces, out.v_offset, out.f_offset, float(x0))
+        del out
+        if rank == 0:
+            torch.cuda.empty_cache()
+            big = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+            for xs in range(0, n, 256):
+                big[xs:xs + 256] = gyroid_cuda(n, xs, min(xs + 256, n), dev)
+            desc1 = capi.McDesc.make(big.shape, 0.0)
+            for _ in range(2):
+                o1 = capi.mc_extract(desc1, big, V_tot + V_tot // 16, F_tot + F_tot // 16)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                o1 = capi.mc_extract(desc1, big, V_tot + V_tot // 16, F_tot + F_tot // 16)
+            b.record()
+            torch.cuda.synchronize()
+            t1 = a.elapsed_time(b) / 5
+            del big
+            one = verify.mesh_checksums(o1[0], o1[1], single=True)
+            strong = {"t1_ms": t1, "tN_ms": ms, "speedup": t1 / ms, "efficiency": t1 / ms / world,
+                      "note": "t1 = the same grid on one GPU (rank 0), same job, p3d_mc_extract"}
+            verification = {"vertex_checksum": f"{sums[0]:016x}", "triangle_checksum": f"{sums[1]:016x}",
+                            "single_gpu_vertex_checksum": f"{one[0]:016x}", "single_gpu_triangle_checksum": f"{one[1]:016x}",
+                            "equals_single_gpu": tuple(sums) == tuple(one) and (o1[2], o1[3]) == (V_tot, F_tot),
+                            "what": "primitive3d_b200/verify.py: vertex multiset hash and order-sensitive triangle hash "
+                                    "(corner coordinates, global face order), independent of the vertex numbering"}
+            assert verification["equals_single_gpu"], verification
+            del o1
+            torch.cuda.empty_cache()
+        dist.barrier()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -357,17 +397,19 @@ def main():
     kernels = {k: {"ms": k_ms[k], "algorithmic_bytes": k_bytes[k], "achieved_gbs": k_bytes[k] / (k_ms[k] * 1e-3) / 1e9,
                    "share_of_step": k_ms[k] / sum(k_ms.values())} for k in k_ms}
     dom = max(k_ms, key=k_ms.get)
-    line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "faces": "k_faces"}[dom],
+    line["roofline"] = {"bound": "hbm", "kernel": {"tile_pass": "k_tile", "faces": "k_faces_rows"}[dom],
                         "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": kernels[dom]["achieved_gbs"] / peak,
-                        "traffic": ncu_traffic({"tile_pass": "k_tile", "faces": "k_faces"}[dom], n) if world == 1 else None,
-                        "peak_source": peak_src,
+                        "traffic": ncu_traffic({"tile_pass": "k_tile", "faces": "k_faces_rows"}[dom], slab.shape[0]),
+                        "path_frac": line["path"]["frac_of_peak"], "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": k_bytes[dom], "launch_ms": k_ms[dom]}
     line["kernels"] = kernels
     line["host_overhead_ms_per_step"] = ms - sum(k_ms.values()) if world == 1 else None
     del verts, faces, ws
 
     line["e2e"] = e2e
+    if strong:
+        line["strong_scaling"], line["verification"] = strong, verification
     if not args.no_extras and world == 1:
         import prim3d
         # ---- the reference's own CUDA kernels on this GPU (largest size its int32 indexing allows here) ----
@@ -388,8 +430,7 @@ def main():
                 from primitive3d_b200 import workloads as oin   # input generators only
                 small = {"sphere128": torch.from_numpy(oin.sphere_int64(128).astype(np.float32)).to(dev),
                          "bunny66": torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "mc_bunny66.npz"))["grid"]).to(dev)}
-                small["bunny256"] = torch.nn.functional.interpolate(small["bunny66"][None, None], size=(256,) * 3,
-                                                                    mode="trilinear", align_corners=True)[0, 0].contiguous()
+                small["bunny256"] = torch.from_numpy(oin.upsample_trilinear(small["bunny66"].cpu().numpy(), 256)).to(dev)
                 line["reference_cuda_examples"] = {}
                 for name, gs in small.items():
                     box = [float(v) for v in gs.shape]

@@ -195,6 +195,22 @@ p3d_status p3d_mc_export_exchange(const p3d_mc_desc *desc, const void *workspace
 p3d_status p3d_mc_faces_exchanged(const p3d_mc_desc *desc, void *workspace, const uint32_t *gathered, int rank,
                                   int world, int32_t *faces, int64_t face_capacity, void *stream);
 
+/* The whole multi-GPU extraction of ONE shard as one call (what primitive3d_b200/sharded.py does through the three
+ * calls above, for C / C++ callers that hold an NCCL communicator): tile pass -> payload -> ncclAllGather over
+ * `nccl_comm` (an ncclComm_t of `world` ranks, this process being `rank`; NCCL is resolved at run time from the
+ * libnccl.so.2 already loaded in the process, else from the default library path) -> vertex id base and halo
+ * numbering on the device -> face pass, all queued on `stream`; the host waits once, for the counts.
+ *   exchange_send  device uint32[p3d_mc_exchange_words(desc)], exchange_recv device uint32[world * that]: scratch
+ *   counts_host    int64[2 * world] = {V_0, F_0, V_1, F_1, ...}: this shard's vertices are global ids
+ *                  [sum of V_r below rank, + V_rank), its faces (GLOBAL vertex ids) start at the sum of F_r below rank
+ * Capacities as in p3d_mc_extract (vertices beyond vertex_capacity are not written: redo with p3d_mc_vertices;
+ * nothing is written to `faces` if F_rank exceeds face_capacity: redo with p3d_mc_faces and the vertex id base).
+ * The reference has no multi-GPU path; this is the dim-0 slab sharding of SURVEY.md section 8(e). */
+p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                                  size_t workspace_bytes, void *nccl_comm, int rank, int world, uint32_t *exchange_send,
+                                  uint32_t *exchange_recv, float *vertices, int64_t vertex_capacity, int32_t *faces,
+                                  int64_t face_capacity, int64_t *counts_host, void *stream);
+
 /* Marching cubes of a grid in HOST memory, pipelined slab by slab on one device: while slab k is
  * extracted, slab k+1 uploads and the mesh of slab k-1 downloads, so the call costs about
  * max(upload, download) instead of upload + compute + download (the reference wrapper's

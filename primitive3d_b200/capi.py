@@ -74,6 +74,9 @@ def lib():
         L.p3d_mc_export_exchange.argtypes = [dp, vp, vp, vp]
         L.p3d_mc_faces_exchanged.restype = ctypes.c_int
         L.p3d_mc_faces_exchanged.argtypes = [dp, vp, vp, ctypes.c_int, ctypes.c_int, vp, i64, vp]
+        L.p3d_mc_sharded_extract.restype = ctypes.c_int
+        L.p3d_mc_sharded_extract.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, i64, vp, i64,
+                                             ctypes.POINTER(i64), vp]
         L.p3d_mc_extract_host.restype = ctypes.c_int
         L.p3d_mc_extract_host.argtypes = [dp, vp, ctypes.c_int, i64, vp, i64, vp, i64, ctypes.POINTER(i64), vp, sz]
         L.p3d_mc_extract_host_arena_bytes.restype = sz

@@ -4,7 +4,9 @@
 // triangle counts per piece and per chunk).
 //
 // A warp takes a task = a run of consecutive (x, y) rows of the grid in voxel-major order and walks it row by
-// row; lane l owns the bit words l, l + 32, ... of the row (NW words per lane, rows of up to 128 words).  The
+// row; lane l owns bit word l of the row -- of its WINDOW of the row when rows are longer than 32 words (1024
+// samples): a task is then (run of rows, window), and what the other windows of a row contribute to the face
+// offset comes from the per-piece triangle counts.  The
 // eight crossing masks a cell's twelve edges live in,
 //   q0 (x,y) x-edges   q1 (x,y) y-edges   q2 (x,y) z-edges   q3 (x+1,y) y-edges
 //   q4 (x+1,y) z-edges q5 (x,y+1) x-edges q6 (x,y+1) z-edges q7 (x+1,y+1) z-edges
@@ -86,6 +88,7 @@ struct RowKeep {
     uint32_t own[NW];             // OR of the row's own crossing masks
     uint32_t vya[NW], vyb[NW];    // id of the first y-edge vertex of the piece, rows (x, y) and (x + 1, y)
     uint32_t nfw[NW];             // triangles of the word's cells (0 for rows without cells)
+    uint32_t skip;                // packed triangle counts of a piece between my window of this row and of the next row
 };
 
 // what a row reads from global memory
@@ -93,6 +96,8 @@ template <int NW>
 struct RowLoad {
     uint32_t a[NW], b[NW], nfp[NW];
     uint32_t eax[NW], eay[NW], eaz[NW], eby[NW], ebz[NW];
+    uint32_t an31, bn31;          // lane 31: the first words of the next window of the row (rows of several windows)
+    uint32_t skip;
 };
 
 // corner bits a0 a1 b0 b1 c0 c1 d0 d1 of the cell at bit i (x0 = sample z, x1 = sample z + 1)
@@ -102,10 +107,11 @@ __device__ __forceinline__ uint32_t corner_code_rows(uint32_t a, uint32_t an, ui
            ((__funnelshift_r(d, dn, i) & 3u) << 6);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
+// MULTI: rows of more than 32 bit words (several windows per row)
+template <int NW, bool MULTI>
+__global__ void __launch_bounds__(kRowWarps * 32, P3D_ROWS_CTAS)
     k_faces_rows(McGeom g, McWorkspace ws, int32_t vbase_arg, int32_t *__restrict__ faces, unsigned long long face_capacity,
-                 int vertex_base_from_header, int rows_per_task, uint32_t ntasks) {
+                 int vertex_base_from_header, int rows_per_task, uint32_t ntasks, int windows) {
     uint32_t vbase = (uint32_t)vbase_arg;
     if (vertex_base_from_header) vbase += (uint32_t)ws.header->vertex_base;  // multi-GPU: computed by k_apply_exchange
     // speculative launch (p3d_mc_extract): nothing is written if the buffer is too small
@@ -139,18 +145,10 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
     const int64_t nrows = g.owned_x * g.ry;  // rows whose cells this launch owns
     const int64_t allrows = g.rx * g.ry;     // rows present in the bit words / the table
     const int w4 = lane & 3;
-    bool valid[NW];
-    uint32_t zv[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-        valid[k] = 32 * k + lane < W;
-        zv[k] = low_mask_rows(rz - 1 - 32 * (32 * k + lane));  // samples with z + 1 < rz
-    }
-
     // word after (k, lane) in the row
-    auto next_word = [&](const uint32_t (&v)[NW], int k) {
+    auto next_word = [&](const uint32_t (&v)[NW], int k, uint32_t of_lane31 = 0u) {
         const uint32_t t = __shfl_down_sync(kFull, v[k], 1);
-        const uint32_t u = k + 1 < NW ? __shfl_sync(kFull, v[k + 1 < NW ? k + 1 : k], 0) : 0u;
+        const uint32_t u = k + 1 < NW ? __shfl_sync(kFull, v[k + 1 < NW ? k + 1 : k], 0) : of_lane31;
         return lane == 31 ? u : t;
     };
     // exclusive prefix over the words of a piece (4 adjacent lanes) of 8-bit packed counts
@@ -170,15 +168,27 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
         const uint32_t task = __shfl_sync(kFull, ticket_ahead, 0);
         if (task >= ntasks) break;
         if (lane == 0) ticket_ahead = atomicAdd(&ws.header->ticket_faces, 1u);
-        const int64_t R0 = (int64_t)task * rows_per_task;
+        const int win = MULTI ? (int)(task % (uint32_t)windows) : 0;  // my 32 words of the rows
+        const int64_t R0 = (int64_t)(MULTI ? task / (uint32_t)windows : task) * rows_per_task;
         const int nr = (int)(nrows - R0 < rows_per_task ? nrows - R0 : rows_per_task);
-        const int64_t P0 = R0 * np;
+        const int64_t P0 = R0 * np + 8 * win;             // first piece of the task
+        const int word0 = 32 * win;
+        const bool more = MULTI && word0 + 32 < W;        // the rows go on after my window
+        const int pw = np - 8 * win < 8 ? np - 8 * win : 8;  // pieces of my window
+        const int nskip = MULTI ? np - pw : 0;            // pieces between my window of a row and of the next row (<= 31)
+        bool valid[NW];
+        uint32_t zv[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            valid[k] = word0 + 32 * k + lane < W;
+            zv[k] = low_mask_rows(rz - 1 - 32 * (word0 + 32 * k + lane));  // samples with z + 1 < rz
+        }
 
         // ---- everything a row reads from global memory, issued as one batch; the pointers walk down the task's rows
         // (stepped in place: an address register that is rewritten right after its load stalls on the load) ----
-        const uint32_t *pa = ws.bits + R0 * W + lane, *pb = pa + g.ry * W;
+        const uint32_t *pa = ws.bits + R0 * W + word0 + lane, *pb = pa + g.ry * W;
         const uint4 *qa = ws.ptab + P0 + (lane >> 2), *qb = qa + g.ry * np;
-        const uint32_t *pn = ws.nf + P0 + (lane >> 2);
+        const uint32_t *pn = ws.nf + P0 + (lane >> 2), *ps = ws.nf + P0 + pw + lane;
         const int64_t want = (int64_t)nr + 2;
         const int rows_a = (int)(allrows - R0 < want ? allrows - R0 : want);
         const int rows_b = (int)(allrows - g.ry - R0 < want ? allrows - g.ry - R0 : want);
@@ -188,6 +198,13 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
             for (int k = 0; k < NW; ++k) {
                 L.a[k] = L.b[k] = L.nfp[k] = 0u;
                 L.eax[k] = L.eay[k] = L.eaz[k] = L.eby[k] = L.ebz[k] = 0u;
+                L.an31 = L.bn31 = L.skip = 0u;
+                if (more) {  // the word after lane 31's is in the next window
+                    if (lane == 31 && rload < rows_a) L.an31 = __ldg(pa + 1);
+                    if (lane == 31 && rload < rows_b) L.bn31 = __ldg(pb + 1);
+                }
+                // the pieces between my window of this row and my window of the next row of the task
+                if (lane < nskip && rload + 1 < nr) L.skip = __ldg(ps);
                 if (valid[k] && rload < rows_a) {
                     L.a[k] = __ldg(pa + 32 * k);
                     const uint4 e = __ldg(qa + 8 * k);
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
                 }
             }
             ++rload;
-            pa += W, pb += W, qa += np, qb += np, pn += np;
+            pa += W, pb += W, qa += np, qb += np, pn += np, ps += np;
         };
         // a row's own part: x-edge and z-edge masks (:29-33, :41-45) with the ids of their first crossings, written to
         // quad t & 1 of the lane's slots (t = row of the task)
@@ -213,8 +230,8 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
             }
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
-                o.an[k] = next_word(o.a, k);
-                o.bn[k] = next_word(o.b, k);
+                o.an[k] = next_word(o.a, k, L.an31);
+                o.bn[k] = next_word(o.b, k, L.bn31);
                 const uint32_t a2 = __funnelshift_r(o.a[k], o.an[k], 1), b2 = __funnelshift_r(o.b[k], o.bn[k], 1);
                 const uint32_t xm = o.a[k] ^ o.b[k];  // ranks are used for rows with x + 1 < rx only
                 const uint32_t za = (o.a[k] ^ a2) & zv[k], zb = (o.b[k] ^ b2) & zv[k];
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
                 o.vyb[k] = L.eby[k] + vbase;
                 o.nfw[k] = (L.nfp[k] >> (8 * w4)) & 255u;  // 0 for rows without cells (x + 1 == rx or y + 1 == ry)
             }
+            o.skip = L.skip;
         };
 
         RowLoad<NW> L;
@@ -358,11 +376,17 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
                     const uint32_t flip = 4u * (uint32_t)(j & 1);
 #pragma unroll
                     for (int k = 0; k < NW; ++k) {
-                        const uint32_t xay = next_word(cur.vya, k), xby = next_word(cur.vyb, k);
+                        uint32_t xay = next_word(cur.vya, k), xby = next_word(cur.vyb, k);
                         if (w4 == 3 && (act[k] >> 31)) {
                             // the next word's first x-edge ids: pair 0 of its lower / upper quad
                             const uint4 *nk = &sc.rank[(32 * k + lane + 1) * (kSlotBytes / 16)];
-                            const uint32_t xax = nk[2 * (j & 1)].y, xdx = nk[2 * ((j + 1) & 1)].y;
+                            uint32_t xax = nk[2 * (j & 1)].y, xdx = nk[2 * ((j + 1) & 1)].y;
+                            if (lane == 31) {  // ... which another task handles: its table entries (rows j and j + 1 of mine)
+                                const uint4 *e = ws.ptab + P0 + (int64_t)j * np + 8;
+                                const uint4 ea = __ldg(e), ed = __ldg(e + np);
+                                xax = ea.x + vbase, xay = ea.y + vbase, xdx = ed.x + vbase;
+                                xby = __ldg(e + g.ry * np).y + vbase;
+                            }
                             const uint2 tt = table[corner_code_rows(cur.a[k], cur.an[k], cur.b[k], cur.bn[k], nxt.b[k], nxt.bn[k],
                                                                     nxt.a[k], nxt.an[k], 31)];
                             const uint32_t nt = tt.y >> 28;
@@ -384,20 +408,22 @@ __global__ void __launch_bounds__(kRowWarps * 32, NW == 1 ? P3D_ROWS_CTAS : 2)
 #if P3D_ROWS_LATE_LOADS
             else if (j + 1 < nr) load_row(L);
 #endif
+            // rows of several windows: the triangles of the other windows' pieces before my window of the next row
+            if (nskip) frun += __reduce_add_sync(kFull, __dp4a(cur.skip, 0x01010101u, 0u));
             cur = nxt;
         }
     }
 }
 
-template <int NW>
+template <int NW, bool MULTI>
 void launch_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
                  bool vertex_base_from_header, cudaStream_t s) {
     constexpr int smem = 512 * (int)sizeof(uint2) + kRowWarps * (int)sizeof(RowScratch<NW>);
     static int cache[kMaxDevices];
     const int per_sm = per_device(cache, [] {
-        cudaFuncSetAttribute(k_faces_rows<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_faces_rows<NW, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int n = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_faces_rows<NW>, kRowWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_faces_rows<NW, MULTI>, kRowWarps * 32, smem);
         return n > 0 ? n : 1;
     });
     const int64_t nrows = g.owned_x * g.ry;
@@ -406,31 +432,36 @@ void launch_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, 
     int rpt = 32;
     if (const char *e = getenv("P3D_ROWS_PER_TASK")) rpt = atoi(e) > 0 ? atoi(e) : rpt;  // tuning runs
     const int64_t warps = (int64_t)sm_count() * per_sm * kRowWarps;
-    while (rpt > 2 && nrows / rpt < 4 * warps) rpt /= 2;
-    const int64_t ntasks = (nrows + rpt - 1) / rpt;
+    const int windows_ = (4 * g.np + 31) / 32;
+    while (rpt > 2 && nrows / rpt * windows_ < 4 * warps) rpt /= 2;
+    const int windows = (4 * g.np + 31) / 32;  // tasks of a run of rows: one per 32 bit words of a row
+    const int64_t ntasks = (nrows + rpt - 1) / rpt * windows;
     const int64_t want = (ntasks + kRowWarps - 1) / kRowWarps, cap = (int64_t)sm_count() * per_sm;
-    k_faces_rows<NW><<<(unsigned)(want < cap ? want : cap), kRowWarps * 32, smem, s>>>(
+    k_faces_rows<NW, MULTI><<<(unsigned)(want < cap ? want : cap), kRowWarps * 32, smem, s>>>(
         g, ws, p.vertex_id_base, faces, (unsigned long long)face_capacity, vertex_base_from_header ? 1 : 0, rpt,
-        (uint32_t)ntasks);
+        (uint32_t)ntasks, windows);
 }
 
 }  // namespace
 
 bool faces_rows_applicable(const McGeom &g) {
+    // P3D_MC_FACES = chunks / rows forces one form of the face pass where both apply (A/B runs, tests)
     static const int mode = [] {
-        const char *e = getenv("P3D_MC_FACES");  // "chunks" forces the chunk form (A/B runs, tests)
-        return e && e[0] == 'c' ? 0 : 1;
+        const char *e = getenv("P3D_MC_FACES");
+        return !e ? 1 : (e[0] == 'c' ? 0 : (e[0] == 'r' ? 2 : 1));
     }();
     const int W = 4 * g.np;
-    return mode == 1 && W > 16 && W <= 128 && g.npieces > 0;
+    // rows of 17 bit words or more, 32 words per task (the pieces a task skips between two rows are one per lane: <= 31)
+    const bool can = W > 16 && g.np <= 39 && g.npieces > 0;
+    // by default only rows of ONE window (rz <= 1024): on longer rows the chunk form, which gives a lane two words of
+    // a row, measured faster (gyroid 2048^3 slab of 257 planes: 0.53 against 0.60 ms)
+    return can && (mode == 2 || (mode == 1 && W <= 32));
 }
 
 void launch_faces_rows(const McGeom &g, const McWorkspace &ws, const McEmitParams &p, int32_t *faces, int64_t face_capacity,
                        bool vertex_base_from_header, cudaStream_t s) {
-    const int W = 4 * g.np;
-    if (W <= 32) launch_rows<1>(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
-    else if (W <= 64) launch_rows<2>(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
-    else launch_rows<4>(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
+    if (4 * g.np <= 32) launch_rows<1, false>(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
+    else launch_rows<1, true>(g, ws, p, faces, face_capacity, vertex_base_from_header, s);
 }
 
 }  // namespace p3d

@@ -4,6 +4,7 @@
 #include "../../include/prim3d_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <climits>
 #include <cstdio>
@@ -350,6 +351,53 @@ p3d_status p3d_mc_faces_exchanged(const p3d_mc_desc *desc, void *workspace, cons
     p3d::launch_apply_exchange(g, ws, gathered, rank, world, s);
     if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, true, s);
     P3D_CUDA(cudaGetLastError());
+    return P3D_OK;
+}
+
+namespace {
+// ncclAllGather, resolved at run time: the library links against no NCCL (torch brings its own copy)
+typedef int (*NcclAllGatherFn)(const void *, void *, size_t, int /* ncclDataType_t */, void * /* ncclComm_t */, cudaStream_t);
+NcclAllGatherFn nccl_all_gather() {
+    static NcclAllGatherFn fn = [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already uses, if any
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        return h ? reinterpret_cast<NcclAllGatherFn>(dlsym(h, "ncclAllGather")) : nullptr;
+    }();
+    return fn;
+}
+}  // namespace
+
+p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, size_t workspace_bytes,
+                                  void *nccl_comm, int rank, int world, uint32_t *exchange_send, uint32_t *exchange_recv,
+                                  float *vertices, int64_t vertex_capacity, int32_t *faces, int64_t face_capacity,
+                                  int64_t *counts_host, void *stream) {
+    if (!nccl_comm || !exchange_send || !exchange_recv || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract: null pointer");
+    if (world < 1 || rank < 0 || rank >= world) return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract: bad rank / world");
+    NcclAllGatherFn gather = nccl_all_gather();
+    if (!gather) return fail(P3D_ERR_CUDA, "p3d_mc_sharded_extract: libnccl.so.2 (ncclAllGather) not found");
+    const int64_t words = p3d_mc_exchange_words(desc);
+    if (words <= 0) return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract: invalid descriptor");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    p3d_status st = p3d_mc_tile_async(desc, grid, dtype, workspace, workspace_bytes, vertices, vertex_capacity, stream);
+    if (st != P3D_OK) return st;
+    st = p3d_mc_export_exchange(desc, workspace, exchange_send, stream);
+    if (st != P3D_OK) return st;
+    const int rc = gather(exchange_send, exchange_recv, (size_t)words, 2 /* ncclInt32 */, nccl_comm, s);
+    if (rc != 0) return fail(P3D_ERR_CUDA, "p3d_mc_sharded_extract: ncclAllGather failed with code " + std::to_string(rc));
+    st = p3d_mc_faces_exchanged(desc, workspace, exchange_recv, rank, world, faces, face_capacity, stream);
+    if (st != P3D_OK) return st;
+    // the last four words of every shard's payload are its {V, F}: one strided copy, the only synchronisation
+    int64_t *pin = pinned_counts((size_t)world);
+    if (!pin) return fail(P3D_ERR_CUDA, "p3d_mc_sharded_extract: pinned allocation failed");
+    P3D_CUDA(cudaMemcpy2DAsync(pin, 16, exchange_recv + (words - 4), (size_t)words * 4, 16, (size_t)world,
+                               cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaStreamSynchronize(s));
+    int64_t total_v = 0;
+    for (int i = 0; i < 2 * world; ++i) counts_host[i] = pin[i];
+    for (int r = 0; r < world; ++r) total_v += counts_host[2 * r];
+    if (total_v > INT32_MAX)
+        return fail(P3D_ERR_OVERFLOW, "p3d_mc_sharded_extract: global vertex count exceeds the int32 face-index contract");
     return P3D_OK;
 }
 

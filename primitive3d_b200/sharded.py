@@ -164,3 +164,83 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
     verts = capi.mc_vertices(desc, slab, ws, V, vbuf)       # exact-size second pass only if the guess was too small
     faces = fbuf[:F] if F <= face_capacity else capi.mc_faces(desc, ws, F, v_off)   # halo numbering is installed
     return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)
+
+
+# ---------------------------------------------------------------------------------------------
+# The same extraction through the single C entry p3d_mc_sharded_extract, over a raw NCCL communicator
+# (what a C / C++ host would do; torch.distributed only carries the unique id to the other ranks).
+# ---------------------------------------------------------------------------------------------
+class _NcclUniqueId(ctypes.Structure):
+    _fields_ = [("internal", ctypes.c_byte * 128)]
+
+
+def _nccl():
+    """The libnccl.so.2 torch itself uses (already loaded once torch.distributed's NCCL backend is up)."""
+    for name in ("libnccl.so.2",):
+        try:
+            return ctypes.CDLL(name, mode=ctypes.RTLD_GLOBAL)
+        except OSError:
+            pass
+    import glob
+    import os
+    hits = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
+    if not hits:
+        raise ImportError("libnccl.so.2 not found")
+    return ctypes.CDLL(hits[0], mode=ctypes.RTLD_GLOBAL)
+
+
+def nccl_comm_init(group=None):
+    """A raw ncclComm_t (as an int) spanning the ranks of `group`, on the current CUDA device."""
+    nccl = _nccl()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = _NcclUniqueId()
+    if rank == 0:
+        if nccl.ncclGetUniqueId(ctypes.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+    box = [bytes(uid.internal)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctypes.memmove(ctypes.byref(uid), box[0], 128)
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _NcclUniqueId, ctypes.c_int]
+    if nccl.ncclCommInitRank(ctypes.byref(comm), world, uid, rank) != 0:
+        raise RuntimeError("ncclCommInitRank failed")
+    return comm.value
+
+
+def nccl_comm_destroy(comm):
+    nccl = _nccl()
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    nccl.ncclCommDestroy(ctypes.c_void_p(comm))
+
+
+def marching_cubes_slab_c(slab, thresh, x_begin, global_rx, comm, rank, world, vertex_capacity=None, face_capacity=None):
+    """marching_cubes_slab through ONE C call (p3d_mc_sharded_extract) over the raw communicator `comm`."""
+    x0, x1 = slab_range(global_rx, world, rank)
+    if x0 != x_begin or slab.shape[0] != min(x1 + 1, global_rx) - x0:
+        raise ValueError(f"rank {rank}: slab must hold planes [{x0}, {min(x1 + 1, global_rx)})")
+    ry, rz = slab.shape[1], slab.shape[2]
+    desc = capi.McDesc.make(slab.shape, thresh, [0.0, 0.0, 0.0], [float(global_rx), float(ry), float(rz)], owned_x=x1 - x0,
+                            x_origin=x0, global_rx=global_rx)
+    L = capi.lib()
+    dev = slab.device
+    ws_bytes, hint = capi._desc_sizes(desc)
+    vertex_capacity = hint if vertex_capacity is None else int(vertex_capacity)
+    face_capacity = 2 * vertex_capacity if face_capacity is None else int(face_capacity)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    vbuf = torch.empty((vertex_capacity, 3), dtype=torch.float32, device=dev)
+    fbuf = torch.empty((face_capacity, 3), dtype=torch.int32, device=dev)
+    words = L.p3d_mc_exchange_words(ctypes.byref(desc))
+    send = torch.empty(words, dtype=torch.int32, device=dev)
+    recv = torch.empty(world * words, dtype=torch.int32, device=dev)
+    counts = (ctypes.c_int64 * (2 * world))()
+    with capi._on_device(dev):
+        capi.check(L.p3d_mc_sharded_extract(ctypes.byref(desc), slab.data_ptr(), capi._grid_ok(slab), ws.data_ptr(), ws.numel(),
+                                            ctypes.c_void_p(comm), rank, world, send.data_ptr(), recv.data_ptr(),
+                                            vbuf.data_ptr(), vertex_capacity, fbuf.data_ptr(), face_capacity, counts,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    pairs = [(counts[2 * r], counts[2 * r + 1]) for r in range(world)]
+    V, F = pairs[rank]
+    v_off, f_off, v_tot, f_tot = exclusive_offsets(pairs, rank)
+    verts = capi.mc_vertices(desc, slab, ws, V, vbuf)
+    faces = fbuf[:F] if F <= face_capacity else capi.mc_faces(desc, ws, F, v_off)
+    return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)

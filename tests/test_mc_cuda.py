@@ -348,6 +348,30 @@ def test_generic_loader_matches_tma(monkeypatch):
     assert np.array_equal(outs[0]["f"], outs[1]["f"])
 
 
+@pytest.mark.parametrize("shape", [(6, 7, 1024), (5, 9, 700), (3, 4, 2100), (9, 40, 2048), (3, 3, 4992)])
+def test_both_forms_of_the_face_pass_agree(shape):
+    """The face pass exists in a row-streaming form (mc_faces_rows.cu; the default for rows of up to 1024 samples)
+    and in the chunk form (k_faces); P3D_MC_FACES forces one of them where both apply.  Same vertex numbering, so
+    the face arrays are identical -- and equal to the oracle's triangles."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from oracle import inputs; from primitive3d_b200 import capi;"
+            "g = torch.from_numpy(inputs.noise(%r, 31)).cuda();"
+            "v, f = capi.marching_cubes(g, 0.0); torch.cuda.synchronize();"
+            "np.savez(sys.argv[1], v=v.cpu().numpy(), f=f.cpu().numpy())") % (os.path.dirname(HERE), HERE, tuple(shape))
+    outs = []
+    for mode in ["rows", "chunks"]:
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"p3d_faces_{mode}_{os.getpid()}.npz")
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, P3D_MC_FACES=mode))
+        outs.append(np.load(path))
+        os.remove(path)
+    assert np.array_equal(outs[0]["v"].view(np.uint32), outs[1]["v"].view(np.uint32))
+    assert np.array_equal(outs[0]["f"], outs[1]["f"])
+    ov, of = mc.marching_cubes(inputs.noise(tuple(shape), 31), 0.0)
+    assert_same_mesh(outs[0]["v"], outs[0]["f"], ov, of, ordered_faces=True)
+
+
 @pytest.mark.parametrize("n,V,F", [(512, 10111488, 20157724)])
 def test_gyroid_known_counts_large(n, V, F):
     """SURVEY.md Appendix B known answers at a size the oracle still checks in seconds."""

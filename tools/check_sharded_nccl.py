@@ -28,6 +28,17 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     out = sharded.marching_cubes_slab(slab, 0.0, x0, n)
     torch.cuda.synchronize()
+    # the same shard through the single C entry p3d_mc_sharded_extract over a raw NCCL communicator
+    comm = sharded.nccl_comm_init()
+    out_c = sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world)
+    torch.cuda.synchronize()
+    assert (out_c.v_offset, out_c.f_offset, out_c.num_vertices_total, out_c.num_faces_total) == \
+        (out.v_offset, out.f_offset, out.num_vertices_total, out.num_faces_total)
+    assert torch.equal(out_c.vertices.view(torch.int32), out.vertices.view(torch.int32)) and torch.equal(out_c.faces, out.faces)
+    sharded.nccl_comm_destroy(comm)
+    # numbering-independent checksums of the sharded mesh (primitive3d_b200/verify.py), taken shard-wise
+    from primitive3d_b200 import verify
+    sums = verify.mesh_checksums(out.vertices, out.faces, out.v_offset, out.f_offset, float(x0))
     shards = [None] * world
     dist.all_gather_object(shards, (out.vertices.cpu(), out.faces.cpu(), out.v_offset, out.f_offset))
     if rank == 0:
@@ -39,7 +50,9 @@ def main():
         assert (out.num_vertices_total, out.num_faces_total) == (v.shape[0], f.shape[0])
         assert torch.equal(vs.view(torch.int32), v.cpu().view(torch.int32)), "vertices differ"
         assert torch.equal(fs, f.cpu()), "faces differ"
-        print(f"sharded NCCL check OK: world={world} n={n} V={v.shape[0]} F={f.shape[0]}")
+        assert verify.mesh_checksums(v, f, single=True) == sums, "checksums of the sharded and the single-GPU mesh differ"
+        print(f"sharded NCCL check OK: world={world} n={n} V={v.shape[0]} F={f.shape[0]} "
+              f"(python driver == p3d_mc_sharded_extract == single GPU; checksums {sums[0]:016x} {sums[1]:016x})")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--noise", action="store_true", help="uniform-noise grid instead of the gyroid")
+    ap.add_argument("--planes", type=int, default=0, help="only the first PLANES dim-0 planes of the gyroid (a multi-GPU slab)")
     args = ap.parse_args()
     import torch
     from bench import gyroid_cuda
@@ -33,8 +34,8 @@ def main():
     if args.noise:
         g = torch.rand((n, n, n), device=dev) - 0.5
     else:
-        g = gyroid_cuda(n, 0, n, dev)
-    desc = capi.McDesc.make(g.shape, 0.0)
+        g = gyroid_cuda(n, 0, args.planes or n, dev)
+    desc = capi.McDesc.make(g.shape, 0.0, [0.0, 0.0, 0.0], [float(n)] * 3, global_rx=n)
     V, F, ws, vbuf = capi.mc_count(desc, g)
     if vbuf.shape[0] < V:
         V, F, ws, vbuf = capi.mc_count(desc, g, vertex_capacity=V)
@@ -66,7 +67,7 @@ def main():
         wts = torch.arange(flat.numel(), device=dev, dtype=torch.int64) % 65521 + 1
         return int((flat * wts).sum().item() & 0xffffffffffff)
 
-    out = {"size": n, "V": V, "F": F, "vsum": checksum(vbuf[:V]), "fsum": checksum(faces)}
+    out = {"size": n, "planes": int(g.shape[0]), "V": V, "F": F, "vsum": checksum(vbuf[:V]), "fsum": checksum(faces)}
     out["tile_pass_ms"] = timed(lambda: stage(1), before=lambda: stage(0))
     stage(0), stage(1)
     out["tile_vertices_only_ms"] = timed(vert_only)
