@@ -136,6 +136,13 @@ p3d_status p3d_mc_vertices_typed(const p3d_mc_desc *desc, const void *grid, int 
 p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t *faces,
                         int64_t vertex_id_base, void *stream);
 
+/* 1 if p3d_mc_extract handles this grid by its single-launch path (small float32 grids: one kernel for the whole
+ * extraction instead of the tiled passes; off unless the environment sets P3D_MC_SMALL_SINGLE_MAX = samples, because
+ * for ONE grid it measured no faster than the tiled passes -- batches are where it pays, p3d_mc_extract_batch), else 0.  After a single-launch extraction the workspace does NOT hold the
+ * state p3d_mc_vertices / p3d_mc_faces continue from: an output that did not fit its capacity is redone by calling
+ * p3d_mc_extract again with an exact buffer for it (capacity 0 for the output that did fit). */
+int p3d_mc_single_launch(const p3d_mc_desc *desc, int dtype);
+
 /* Whole extraction with ONE host synchronisation (single GPU: owned_x == rx).  Both passes are
  * queued back to back into buffers of speculative capacity; the host waits once, for {V, F}.
  * vertices: float[3*vertex_capacity], faces: int32[3*face_capacity] (device).  On return
@@ -156,6 +163,10 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
  * with the semantics of p3d_mc_extract; counts_host = int64[2*num_grids] = {V_0, F_0, V_1, ...}.
  * The pointer arrays are host arrays of device pointers.  A grid whose output did not fit is
  * redone by the caller with p3d_mc_extract into exact buffers. */
+/* Workspace for p3d_mc_extract_batch: the largest single-grid workspace, or -- when every grid is small enough for
+ * the single-launch path (float32, up to 4 Mi samples each, 64 Mi in total) -- what one launch over the whole batch
+ * needs (32 bytes per 32 samples).  With less, p3d_mc_extract_batch runs the grids one after the other. */
+size_t p3d_mc_batch_workspace_bytes(int64_t num_grids, const p3d_mc_desc *descs);
 p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, const void *const *grids, int dtype,
                                 void *workspace, size_t workspace_bytes, float *const *vertices,
                                 const int64_t *vertex_capacities, int32_t *const *faces,

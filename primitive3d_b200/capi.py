@@ -81,6 +81,10 @@ def lib():
         L.p3d_mc_extract_host.argtypes = [dp, vp, ctypes.c_int, i64, vp, i64, vp, i64, ctypes.POINTER(i64), vp, sz]
         L.p3d_mc_extract_host_arena_bytes.restype = sz
         L.p3d_mc_extract_host_arena_bytes.argtypes = [dp, ctypes.c_int, i64]
+        L.p3d_mc_single_launch.restype = ctypes.c_int
+        L.p3d_mc_single_launch.argtypes = [dp, ctypes.c_int]
+        L.p3d_mc_batch_workspace_bytes.restype = sz
+        L.p3d_mc_batch_workspace_bytes.argtypes = [i64, vp]
         L.p3d_mc_extract_batch.restype = ctypes.c_int
         L.p3d_mc_extract_batch.argtypes = [i64, vp, vp, ctypes.c_int, vp, sz, vp, vp, vp, vp, vp, vp]
         L.p3d_mc_faces.restype = ctypes.c_int
@@ -232,6 +236,16 @@ def mc_extract(desc, grid, vertex_capacity=None, face_capacity=None):
                                    vbuf.data_ptr() if vertex_capacity else None, int(vertex_capacity),
                                    fbuf.data_ptr() if face_capacity else None, int(face_capacity), counts, _stream()))
     V, F = counts[0], counts[1]
+    if lib().p3d_mc_single_launch(ctypes.byref(desc), dtype) and (V > vertex_capacity or F > face_capacity):
+        # small grid (single-launch path): what did not fit is redone by the same call with an exact buffer
+        rv, rf = V > vertex_capacity, F > face_capacity
+        verts = torch.empty((V, 3), dtype=torch.float32, device=grid.device) if rv else vbuf[:V]
+        faces = torch.empty((F, 3), dtype=torch.int32, device=grid.device) if rf else fbuf[:F]
+        with _on_device(grid.device):
+            check(lib().p3d_mc_extract(ctypes.byref(desc), grid.data_ptr(), dtype, ws.data_ptr(), ws.numel(),
+                                       verts.data_ptr() if rv else None, V if rv else 0,
+                                       faces.data_ptr() if rf else None, F if rf else 0, counts, _stream()))
+        return verts, faces, V, F
     verts = mc_vertices(desc, grid, ws, V, vbuf)
     faces = fbuf[:F] if F <= face_capacity else mc_faces(desc, ws, F)
     return verts, faces, V, F
@@ -253,7 +267,7 @@ def marching_cubes_batch(grids, thresh, lower=None, upper=None):
     n = len(grids)
     descs = (McDesc * n)(*[McDesc.make(g.shape, thresh, lower, upper) for g in grids])
     sizes = [_desc_sizes(d) for d in descs]
-    ws = torch.empty(max(s[0] for s in sizes), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(max(s[0] for s in sizes), lib().p3d_mc_batch_workspace_bytes(n, descs)), dtype=torch.uint8, device=dev)
     vcaps, fcaps = [s[1] for s in sizes], [2 * s[1] for s in sizes]
     # one allocation per output kind, carved into per-grid buffers (256-byte aligned starts)
     pad = lambda rows: (rows * 12 + 255) // 256 * 256

@@ -122,6 +122,18 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
         return wasted > std::max<int64_t>(int64_t(64) << 20, n * 12) ? t.clone() : t;
     };
     Tensor vertices, faces;
+    if (p3d_mc_single_launch(&desc, dtype) && (counts[0] > cap || counts[1] > fcap)) {
+        // small grid (single-launch path): what did not fit is redone by the same call with an exact buffer
+        const bool rv = counts[0] > cap, rf = counts[1] > fcap;
+        vertices = rv ? torch::empty({counts[0], 3}, f32_opt) : trimmed(vbuf, counts[0], cap);
+        faces = rf ? torch::empty({counts[1], 3}, i32_opt) : trimmed(fbuf, counts[1], fcap);
+        int64_t again[2] = {0, 0};
+        check_status(p3d_mc_extract(&desc, density_grid.data_ptr(), dtype, workspace.data_ptr(), ws_bytes,
+                                    rv ? vertices.data_ptr<float>() : nullptr, rv ? counts[0] : 0,
+                                    rf ? faces.data_ptr<int32_t>() : nullptr, rf ? counts[1] : 0, again, stream),
+                     "p3d_mc_extract");
+        return {vertices, faces};
+    }
     if (counts[0] <= cap) {
         vertices = trimmed(vbuf, counts[0], cap);
     } else {

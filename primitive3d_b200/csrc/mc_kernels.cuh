@@ -116,6 +116,40 @@ void launch_apply_exchange(const McGeom &g, const McWorkspace &ws, const uint32_
                            cudaStream_t s);
 void launch_export_plane(uint32_t *table_out, const McGeom &g, const McWorkspace &ws, cudaStream_t s);
 void launch_import_halo(const McGeom &g, const McWorkspace &ws, const uint32_t *table_in, uint32_t delta, cudaStream_t s);
+// ---- small grids and batches of them: one kernel launch (mc_small.cu) ----
+constexpr int kSmallMaxCtas = 1024;
+struct SmallGrid {            // one grid of a batch
+    const float *grid;
+    float *vertices;          // nullptr: count only
+    int32_t *faces;
+    int64_t vertex_capacity, face_capacity;
+    int64_t word0;            // index of the grid's first 32-sample word in the batch
+    int32_t rx, ry, rz, wpr;  // wpr = words per row = ceil(rz / 32)
+    float thresh;
+    float scale[3], offset[3];
+};
+struct SmallBatch {
+    int64_t nwords;           // 32-sample words of all grids
+    int32_t ngrids;
+    SmallGrid g0;             // the grid itself when ngrids == 1 (no descriptor array in device memory)
+};
+struct SmallHeader {          // zeroed before the launch
+    unsigned long long total_v, total_f;
+    unsigned int barrier;
+    unsigned int pad[3];
+};
+struct SmallWorkspace {
+    SmallHeader *header;
+    unsigned long long *cta_sums;   // [ctas][2] vertices / faces of a CTA's words
+    unsigned long long *grid_base;  // [ngrids][2] first vertex id / face index of a grid in the batch-wide numbering
+    uint4 *corner;                  // [nwords] inside bits {a, b, c, d} of the four rows of a word's cells
+    uint32_t *cnt;                  // [nwords] nx | ny << 6 | nz << 12 | nf << 18 | next bits << 28
+    uint2 *first;                   // [nwords] batch-wide first vertex id / first face index of a word
+};
+size_t small_workspace_bytes(int64_t nwords, int ngrids);
+SmallWorkspace bind_small(void *base, int64_t nwords, int ngrids, SmallGrid **grids_dev);
+void launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWorkspace &ws, cudaStream_t s);
+
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor
 
 }  // namespace p3d

@@ -7,12 +7,18 @@
 #include <dlfcn.h>
 
 #include <climits>
+#include <cstdlib>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include <string>
 
 #include "mc_kernels.cuh"
 #include "p3d_error.h"
+
+#ifndef P3D_MC_SMALL_MAX_DEFAULT
+#define P3D_MC_SMALL_MAX_DEFAULT (4 << 20)  // samples: grids up to this size take the single-launch path
+#endif
 
 namespace {
 
@@ -111,6 +117,51 @@ p3d::McEmitParams make_params(const p3d_mc_desc *desc, int64_t vertex_id_base) {
     return prm;
 }
 
+// ---- small grids: one kernel launch for the whole extraction (mc_small.cu) ----
+int64_t small_max_samples() {
+    static const int64_t v = [] {
+        const char *e = getenv("P3D_MC_SMALL_MAX");  // samples; 0 sends every grid through the tiled path
+        return e ? (int64_t)atoll(e) : (int64_t)P3D_MC_SMALL_MAX_DEFAULT;
+    }();
+    return v;
+}
+
+// A single grid goes through the single-launch kernel only on request (P3D_MC_SMALL_SINGLE_MAX = samples): measured on
+// B200 its one launch (37 us at bunny 66^3: three latency-bound phases and two device-wide barriers) is no faster
+// than the tiled passes' five (35 us), so the default keeps one numbering for every single-grid entry point.  A
+// BATCH of small grids is where the single launch pays: 64 x 66^3 in 1.0 ms against 3.9 ms one by one.
+int64_t small_single_max_samples() {
+    static const int64_t v = [] {
+        const char *e = getenv("P3D_MC_SMALL_SINGLE_MAX");
+        return e ? (int64_t)atoll(e) : (int64_t)0;
+    }();
+    return v;
+}
+
+inline int64_t small_words(const p3d_mc_desc *d) { return d->rx * d->ry * ((d->rz + 31) / 32); }
+
+bool small_applicable(const p3d_mc_desc *d, int dtype, int64_t max_samples) {
+    return dtype == P3D_F32 && d->rx == d->owned_x && d->x_origin == 0 && d->global_rx == d->rx && d->rx >= 1 && d->ry >= 1 &&
+           d->rz >= 1 && d->rx * d->ry * d->rz <= max_samples;
+}
+bool small_applicable(const p3d_mc_desc *d, int dtype) { return small_applicable(d, dtype, small_max_samples()); }
+bool small_single(const p3d_mc_desc *d, int dtype) { return small_applicable(d, dtype, small_single_max_samples()); }
+
+p3d::SmallGrid small_grid(const p3d_mc_desc *d, const void *grid, float *vertices, int64_t vcap, int32_t *faces, int64_t fcap,
+                          int64_t word0) {
+    const p3d::McEmitParams prm = make_params(d, 0);
+    p3d::SmallGrid g;
+    g.grid = static_cast<const float *>(grid);
+    g.vertices = vcap > 0 ? vertices : nullptr;
+    g.faces = fcap > 0 ? faces : nullptr;
+    g.vertex_capacity = vcap, g.face_capacity = fcap;
+    g.word0 = word0;
+    g.rx = (int32_t)d->rx, g.ry = (int32_t)d->ry, g.rz = (int32_t)d->rz, g.wpr = (int32_t)((d->rz + 31) / 32);
+    g.thresh = d->thresh;
+    for (int i = 0; i < 3; ++i) g.scale[i] = prm.scale[i], g.offset[i] = prm.offset[i];
+    return g;
+}
+
 // One pinned landing pad per host thread for the {V,F} readbacks (grown on demand for batches).
 int64_t *pinned_counts(size_t pairs = 1) {
     thread_local int64_t *buf = nullptr;
@@ -144,7 +195,36 @@ const char *p3d_last_error(void) { return g_last_error.c_str(); }
 size_t p3d_mc_workspace_bytes(const p3d_mc_desc *desc) {
     p3d::McGeom g;
     if (!make_geom(desc, &g)) return 0;
-    return make_layout(g).total;
+    size_t n = make_layout(g).total;
+    if (small_single(desc, P3D_F32)) {
+        const size_t m = p3d::small_workspace_bytes(small_words(desc), 1);
+        if (m > n) n = m;
+    }
+    return n;
+}
+
+int p3d_mc_single_launch(const p3d_mc_desc *desc, int dtype) {
+    p3d::McGeom g;
+    return make_geom(desc, &g) && small_single(desc, dtype) ? 1 : 0;
+}
+
+size_t p3d_mc_batch_workspace_bytes(int64_t num_grids, const p3d_mc_desc *descs) {
+    if (num_grids <= 0 || !descs) return 0;
+    size_t n = 0;
+    int64_t words = 0;
+    bool small = true;
+    for (int64_t i = 0; i < num_grids; ++i) {
+        const size_t m = p3d_mc_workspace_bytes(&descs[i]);
+        if (!m) return 0;
+        if (m > n) n = m;
+        small = small && small_applicable(&descs[i], P3D_F32);
+        words += small_words(&descs[i]);
+    }
+    if (small && words * 32 <= 16 * small_max_samples()) {
+        const size_t m = p3d::small_workspace_bytes(words, (int)num_grids);
+        if (m > n) n = m;
+    }
+    return n;
 }
 
 int64_t p3d_mc_plane_table_words(const p3d_mc_desc *desc) {
@@ -241,6 +321,23 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
     if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_extract: workspace too small");
     if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_extract: workspace must be 256-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (small_single(desc, dtype) && workspace_bytes >= p3d::small_workspace_bytes(small_words(desc), 1)) {
+        // small grid: the whole extraction is ONE kernel launch (mc_small.cu)
+        p3d::SmallGrid *unused = nullptr;
+        const p3d::SmallWorkspace sw = p3d::bind_small(workspace, small_words(desc), 1, &unused);
+        p3d::SmallBatch b;
+        b.nwords = small_words(desc), b.ngrids = 1;
+        b.g0 = small_grid(desc, grid, vertices, vertex_capacity, faces, face_capacity, 0);
+        P3D_CUDA(cudaMemsetAsync(sw.header, 0, sizeof(p3d::SmallHeader), s));
+        p3d::launch_small(b, nullptr, sw, s);
+        P3D_CUDA(cudaGetLastError());
+        int64_t *pin = pinned_counts();
+        int64_t *dst = pin ? pin : counts_host;
+        P3D_CUDA(cudaMemcpyAsync(dst, &sw.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        P3D_CUDA(cudaStreamSynchronize(s));
+        counts_host[0] = dst[0], counts_host[1] = dst[1];
+        return P3D_OK;
+    }
     const p3d::McWorkspace ws = bind(workspace, l);
 
     // everything is queued before the host waits: the face pass starts the moment the tile pass ends
@@ -270,7 +367,7 @@ p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, con
         return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: null pointer");
     if (dtype < P3D_F32 || dtype > P3D_U8) return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: unknown dtype");
     if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: workspace must be 256-byte aligned");
-    int64_t *pin = pinned_counts((size_t)num_grids);
+    int64_t *pin = pinned_counts((size_t)num_grids + 1);
     if (!pin) return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: pinned allocation failed");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (int64_t i = 0; i < num_grids; ++i) {  // validate everything before anything is queued
@@ -281,6 +378,51 @@ p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, con
         if (vertex_capacities[i] < 0 || face_capacities[i] < 0 || (vertex_capacities[i] && !vertices[i]) ||
             (face_capacities[i] && !faces[i]))
             return fail(P3D_ERR_INVALID, "p3d_mc_extract_batch: capacity without a buffer");
+    }
+    // Small grids: ONE kernel launch for the whole batch (mc_small.cu), numbering restarts at every grid.
+    {
+        bool small = dtype == P3D_F32;
+        int64_t words = 0;
+        for (int64_t i = 0; small && i < num_grids; ++i) {
+            small = small_applicable(&descs[i], dtype);
+            words += small_words(&descs[i]);
+        }
+        if (small && words * 32 <= 16 * small_max_samples() && workspace_bytes >= p3d::small_workspace_bytes(words, (int)num_grids)) {
+            p3d::SmallGrid *grids_dev = nullptr;
+            const p3d::SmallWorkspace sw = p3d::bind_small(workspace, words, (int)num_grids, &grids_dev);
+            // descriptors: staged in pinned memory (one buffer per host thread), copied ahead of the launch
+            thread_local p3d::SmallGrid *stage = nullptr;
+            thread_local size_t stage_cap = 0;
+            if ((size_t)num_grids > stage_cap) {
+                if (stage) cudaFreeHost(stage);
+                stage_cap = (size_t)num_grids * 2;
+                if (cudaHostAlloc(reinterpret_cast<void **>(&stage), stage_cap * sizeof(p3d::SmallGrid), cudaHostAllocPortable) != cudaSuccess) {
+                    stage = nullptr, stage_cap = 0;
+                    return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: pinned allocation failed");
+                }
+            }
+            int64_t w0 = 0;
+            for (int64_t i = 0; i < num_grids; ++i) {
+                stage[i] = small_grid(&descs[i], grids[i], vertices[i], vertex_capacities[i], faces[i], face_capacities[i], w0);
+                w0 += small_words(&descs[i]);
+            }
+            p3d::SmallBatch b;
+            b.nwords = words, b.ngrids = (int32_t)num_grids;
+            b.g0 = stage[0];
+            P3D_CUDA(cudaMemsetAsync(sw.header, 0, sizeof(p3d::SmallHeader), s));
+            P3D_CUDA(cudaMemcpyAsync(grids_dev, stage, (size_t)num_grids * sizeof(p3d::SmallGrid), cudaMemcpyHostToDevice, s));
+            p3d::launch_small(b, grids_dev, sw, s);
+            P3D_CUDA(cudaGetLastError());
+            // per-grid counts = differences of the grids' bases (the batch totals close the last one)
+            std::vector<int64_t> base(2 * (size_t)num_grids);
+            P3D_CUDA(cudaMemcpyAsync(pin, sw.grid_base, 2 * (size_t)num_grids * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            P3D_CUDA(cudaMemcpyAsync(pin + 2 * num_grids, &sw.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            P3D_CUDA(cudaStreamSynchronize(s));
+            for (int64_t i = 0; i < num_grids; ++i)
+                for (int k = 0; k < 2; ++k) base[2 * i + k] = pin[2 * (i + 1) + k] - pin[2 * i + k];
+            for (int64_t i = 0; i < 2 * num_grids; ++i) counts_host[i] = base[i];
+            return P3D_OK;
+        }
     }
     // The grids run one after the other on the stream and share the workspace (a grid's face pass has finished
     // with it before the next grid's memset starts); the host waits once, for all the counts.
@@ -466,6 +608,16 @@ p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn a
     float *spec = static_cast<float *>(alloc(alloc_ctx, (size_t)(cap > 0 ? cap : 1) * 12));
     if (!spec) return fail(P3D_ERR_CUDA, "p3d_mc_run: vertex allocation failed");
     int64_t counts[2] = {0, 0};
+    if (p3d_mc_single_launch(desc, P3D_F32)) {  // small grid: count, then both outputs into exact buffers, one launch each
+        p3d_status s1 = p3d_mc_extract(desc, grid, P3D_F32, ws, bytes, nullptr, 0, nullptr, 0, counts, stream);
+        if (s1 != P3D_OK) return s1;
+        *num_vertices = counts[0], *num_faces = counts[1];
+        *vertices = static_cast<float *>(alloc(alloc_ctx, (size_t)(counts[0] > 0 ? counts[0] : 1) * 12));
+        *faces = static_cast<int32_t *>(alloc(alloc_ctx, (size_t)(counts[1] > 0 ? counts[1] : 1) * 12));
+        if (!*vertices || !*faces) return fail(P3D_ERR_CUDA, "p3d_mc_run: output allocation failed");
+        if (counts[0] == 0) return P3D_OK;
+        return p3d_mc_extract(desc, grid, P3D_F32, ws, bytes, *vertices, counts[0], *faces, counts[1], counts, stream);
+    }
     p3d_status st = p3d_mc_count(desc, grid, ws, bytes, spec, cap, counts, stream);
     if (st != P3D_OK) return st;
     *num_vertices = counts[0];

@@ -103,9 +103,10 @@ def test_pybind_module_matches_capi(name):
     v, f = out
     assert v.is_cuda and f.is_cuda and v.dtype == torch.float32 and f.dtype == torch.int32
     assert v.shape[1:] == (3,) and f.shape[1:] == (3,)
+    # the module goes through p3d_mc_extract, which takes the single-launch path for small grids (its own vertex
+    # numbering): same mesh as the staged calls, triangle by triangle
     cv, cf = run_capi(grid, thresh, lower, upper)
-    assert np.array_equal(v.cpu().numpy().view(np.uint32), cv.view(np.uint32))
-    assert np.array_equal(f.cpu().numpy(), cf)
+    assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), cv, cf, ordered_faces=True)
 
 
 def test_python_wrapper_contract():
@@ -189,7 +190,9 @@ def test_single_sync_extraction_equals_staged_calls(name):
     for vcap, fcap in [(None, None), (V0, F0), (V0 + 9, F0 + 9), (max(V0 - 1, 0), F0), (V0, max(F0 - 1, 0)), (3, 5), (0, 0)]:
         v, f, V, F = capi.mc_extract(desc, g, vcap, fcap)
         assert (V, F) == (V0, F0)
-        assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0), (vcap, fcap)
+        # small grids take the single-launch path in p3d_mc_extract (its own vertex numbering): same mesh, triangle by
+        # triangle; whatever did not fit the speculative buffers was redone by the staged calls
+        assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), v0.cpu().numpy(), f0.cpu().numpy(), ordered_faces=True)
 
 
 @pytest.mark.parametrize("nv,nf", [(0, 0), (1, 0), (3, 1), (1001, 333), (4096, 8190)])
@@ -249,14 +252,82 @@ def test_batched_small_grids_equal_one_by_one():
     grids[0] = torch.from_numpy(np.ascontiguousarray(bunny())).cuda()             # smooth: fits the speculative buffers
     out = capi.marching_cubes_batch(grids, 0.0)
     assert len(out) == len(grids)
+    same = lambda a, b: assert_same_mesh(a[0].cpu().numpy(), a[1].cpu().numpy(), b[0].cpu().numpy(), b[1].cpu().numpy(),
+                                         ordered_faces=True)
     for g, (v, f) in zip(grids, out):
-        v0, f0 = capi.marching_cubes(g, 0.0)
-        assert torch.equal(v.view(torch.int32), v0.view(torch.int32)) and torch.equal(f, f0)
+        same((v, f), capi.marching_cubes(g, 0.0))
     assert out[4][0].shape == (0, 3) and out[4][1].shape == (0, 3)
     one_box = capi.marching_cubes_batch(grids[:2], 0.1, [-1.0, -1.0, -1.0], [1.0, 2.0, 3.0])
-    v0, f0 = capi.marching_cubes(grids[1], 0.1, [-1.0, -1.0, -1.0], [1.0, 2.0, 3.0])
-    assert torch.equal(one_box[1][0], v0) and torch.equal(one_box[1][1], f0)
+    same(one_box[1], capi.marching_cubes(grids[1], 0.1, [-1.0, -1.0, -1.0], [1.0, 2.0, 3.0]))
     assert capi.marching_cubes_batch([], 0.0) == []
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_one_call_extraction_matches_oracle(name):
+    """p3d_mc_extract, the entry prim3d.libPrim3D.marching_cubes sits on (the tiled passes, or the single-launch kernel
+    of mc_small.cu when P3D_MC_SMALL_SINGLE_MAX asks for it: tests/test_mc_cuda.py::test_single_launch_kernel_matches_oracle).
+    Against the oracle, triangle by triangle."""
+    from primitive3d_b200 import capi
+    make, thresh, lower, upper = CASES[name]
+    grid = make()
+    g = torch.from_numpy(np.ascontiguousarray(grid)).cuda()
+    v, f, V, F = capi.mc_extract(capi.McDesc.make(g.shape, thresh, lower, upper), g)
+    ov, of = mc.marching_cubes(grid, thresh, lower, upper)
+    assert (V, F) == (ov.shape[0], of.shape[0])
+    assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), ov, of, ordered_faces=True)
+
+
+@pytest.mark.parametrize("name", ["sphere128", "bunny66", "gyroid128", "noise33_s0", "noise65_s2", "noise_flat_tail", "noncubic",
+                                  "ties", "nan_inf", "min222", "thin_x", "thin_y", "thin_z", "thresh_nonzero", "bounds_asym",
+                                  "empty", "full", "noise_piece_edges"])
+def test_single_launch_kernel_matches_oracle(name):
+    """The single-launch kernel on its own (a batch of one grid goes through it): against the oracle, triangle by
+    triangle."""
+    from primitive3d_b200 import capi
+    make, thresh, lower, upper = CASES[name]
+    grid = make()
+    (v, f), = capi.marching_cubes_batch([torch.from_numpy(np.ascontiguousarray(grid)).cuda()], thresh, lower, upper)
+    ov, of = mc.marching_cubes(grid, thresh, lower, upper)
+    assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), ov, of, ordered_faces=True)
+
+
+def test_one_launch_for_a_batch_of_small_grids():
+    """64 bunny-sized grids in ONE kernel launch (p3d_mc_extract_batch on small float32 grids): every mesh equals the
+    oracle's, numbering restarts at every grid."""
+    from primitive3d_b200 import capi
+    base = bunny()
+    grids, want = [], []
+    for i in range(64):
+        g = np.ascontiguousarray(np.roll(base, i, axis=i % 3) * np.float32(1.0 + 0.01 * i))
+        grids.append(torch.from_numpy(g).cuda())
+        if i % 9 == 0:
+            want.append((i, mc.marching_cubes(g, 0.0)))
+    out = capi.marching_cubes_batch(grids, 0.0)
+    assert len(out) == 64
+    for i, (ov, of) in want:
+        assert_same_mesh(out[i][0].cpu().numpy(), out[i][1].cpu().numpy(), ov, of, ordered_faces=True)
+    for v, f in out:
+        assert f.shape[0] == 0 or (int(f.min()) >= 0 and int(f.max()) < v.shape[0])
+
+
+def test_small_path_switch(monkeypatch):
+    """P3D_MC_SMALL_SINGLE_MAX sends single small grids through the single-launch kernel (off by default: for one
+    grid it is no faster than the tiled passes): same mesh as the tiled passes give."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from oracle import inputs; from primitive3d_b200 import capi;"
+            "g = torch.from_numpy(inputs.noise((21, 30, 70), 77)).cuda();"
+            "v, f, V, F = capi.mc_extract(capi.McDesc.make(g.shape, 0.0), g); torch.cuda.synchronize();"
+            "np.savez(sys.argv[1], v=v.cpu().numpy(), f=f.cpu().numpy())") % (os.path.dirname(HERE), HERE)
+    outs = []
+    for limit in ["0", "4194304"]:
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"p3d_small_{limit}_{os.getpid()}.npz")
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, P3D_MC_SMALL_SINGLE_MAX=limit))
+        outs.append(np.load(path))
+        os.remove(path)
+    assert not np.array_equal(outs[0]["f"], outs[1]["f"])       # two numberings ...
+    assert_same_mesh(outs[0]["v"], outs[0]["f"], outs[1]["v"], outs[1]["f"], ordered_faces=True)   # ... of one mesh
 
 
 def test_unsupported_dtype_is_cast_by_the_wrapper():
