@@ -237,7 +237,11 @@ p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int
  *                 aligned (two slabs + their workspaces and output buffers), e.g. from the caller's
  *                 caching allocator; NULL or too small: cudaMalloc / cudaFree inside the call.
  * Vertices are numbered slab by slab (the multi-GPU numbering with world = number of slabs), faces
- * are in voxel-major order with global ids.  Uses its own streams; synchronous for the caller. */
+ * are in voxel-major order with global ids.  Uses its own (non-blocking) streams and is synchronous
+ * for the caller, but does NOT order itself behind work the caller has queued: device work that still
+ * writes `host_grid`, or that still uses the memory handed in as `device_arena` (a block a caching
+ * allocator recycled from a tensor with kernels pending), must have completed before the call --
+ * synchronise that stream first (prim3d / capi.marching_cubes_host do). */
 size_t p3d_mc_extract_host_arena_bytes(const p3d_mc_desc *desc, int dtype, int64_t slab_planes);
 p3d_status p3d_mc_extract_host(const p3d_mc_desc *desc, const void *host_grid, int dtype, int64_t slab_planes,
                                float *host_vertices, int64_t vertex_capacity, int32_t *host_faces,

@@ -31,16 +31,25 @@ class _MarchingTets(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_verts, _gf, _gt, _ge):
         points, sdf, edges = ctx.saved_tensors
-        grad_points, grad_sdf = _C.marching_tetrahedras_backward(points, sdf, edges, grad_verts.contiguous())
+        if grad_verts is None:  # verts took no part in the loss
+            return None, None, None
+        grad_points, grad_sdf = _C.marching_tetrahedras_backward(points, sdf, edges, grad_verts.to(torch.float32).contiguous())
         return grad_points, grad_sdf, None
 
 
 def marching_tetrahedras(vertices, tets, sdf, return_tet_idx=False):
-    """vertices float32 [P,3], tets int64 [T,4] (mutated), sdf float32 [P]
-    -> (verts float32 [V,3], faces int64 [F,3][, tet_idx int64 [F]])."""
+    """vertices float [P,3], tets int64 [T,4] (mutated), sdf float [P]
+    -> (verts [V,3] in the dtype of `vertices`, faces int64 [F,3][, tet_idx int64 [F]]).
+
+    The kernels compute in float32.  Like the reference (dtype-generic torch ops), float64 / float16 / bfloat16
+    inputs get verts and gradients back in their own dtype, through differentiable casts either side of the
+    float32 kernels; anything that is not a floating-point tensor is a TypeError."""
     if not torch.cuda.is_available():
         raise RuntimeError("prim3d.marching_tetrahedras needs a CUDA device")
+    if not vertices.is_floating_point() or not sdf.is_floating_point():
+        raise TypeError("vertices and sdf must be floating-point tensors")
     home = vertices.device
+    out_dtype = vertices.dtype
     staged = not vertices.is_cuda
     points_d = vertices.cuda() if staged else vertices
     sdf_d = sdf.to(points_d.device)
@@ -57,6 +66,8 @@ def marching_tetrahedras(vertices, tets, sdf, return_tet_idx=False):
     if tets_d.data_ptr() != tets.data_ptr():
         with torch.no_grad():
             tets.copy_(tets_d)  # the caller's tensor sees the orientation fix, like the reference
+    if verts.dtype != out_dtype:
+        verts = verts.to(out_dtype)
     if staged:
         verts, faces, tet_idx = verts.to(home), faces.to(home), tet_idx.to(home)
     if return_tet_idx:

@@ -326,6 +326,9 @@ def marching_cubes_host(grid, thresh, lower=None, upper=None, slab_planes=0, ver
             # device scratch from torch's caching allocator: cudaMalloc / cudaFree would cost more than a slab
             nbytes = lib().p3d_mc_extract_host_arena_bytes(ctypes.byref(desc), GRID_DTYPES[grid.dtype], int(slab_planes))
             arena = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            # the call runs on its own streams: whatever the current stream still has queued (a copy into `grid`,
+            # the previous owner of the arena's block) must be over first (include/prim3d_b200.h)
+            torch.cuda.current_stream().synchronize()
             check(lib().p3d_mc_extract_host(ctypes.byref(desc), grid.data_ptr(), GRID_DTYPES[grid.dtype], int(slab_planes),
                                             vertices_out.data_ptr(), vertices_out.shape[0], faces_out.data_ptr(),
                                             faces_out.shape[0], counts, arena.data_ptr(), arena.numel()))

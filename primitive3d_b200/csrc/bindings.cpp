@@ -30,7 +30,7 @@ using torch::Tensor;
 #define P3D_CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")
 
 std::mutex g_capacity_mutex;
-std::map<std::array<int64_t, 3>, std::array<int64_t, 2>> g_last_counts;  // grid shape -> {V, F} of its last extraction
+std::map<std::array<int64_t, 3>, std::array<int64_t, 2>> g_last_counts;  // grid shape -> largest {V, F} seen for it
 
 void check_status(p3d_status st, const char *what) {
     TORCH_CHECK(st == P3D_OK, what, " failed (status ", static_cast<int>(st), "): ", p3d_last_error());
@@ -111,15 +111,17 @@ std::vector<Tensor> marching_cubes(const Tensor &density_grid, const float thres
                  "p3d_mc_extract");
     {
         std::lock_guard<std::mutex> lock(g_capacity_mutex);
+        // a running maximum per shape: alternating thresholds on one shape must not under-size every other call
         if (g_last_counts.size() > 64) g_last_counts.clear();
-        g_last_counts[key] = {counts[0], counts[1]};
+        auto &seen = g_last_counts[key];
+        seen = {std::max(seen[0], counts[0]), std::max(seen[1], counts[1])};
     }
 
     // a view keeps the whole speculative buffer alive: copy out when most of it would be wasted
     auto trimmed = [](const Tensor &buf, int64_t n, int64_t capacity) {
         Tensor t = buf.narrow(0, 0, n);
         const int64_t wasted = (capacity - n) * 12;
-        return wasted > std::max<int64_t>(int64_t(64) << 20, n * 12) ? t.clone() : t;
+        return wasted > std::max<int64_t>(int64_t(1) << 20, n * 3) ? t.clone() : t;  // more than a quarter (and 1 MB) wasted
     };
     Tensor vertices, faces;
     if (p3d_mc_single_launch(&desc, dtype) && (counts[0] > cap || counts[1] > fcap)) {

@@ -5,7 +5,10 @@
 // pairs, masked scatters).  Here:
 //
 //   k_mt_classify   one streaming pass over the tets (32 B each): orientation sign from the
-//                   triple product (p1-p0).((p2-p0)x(p3-p0)) in fp64 (:50-65), in-place swap of
+//                   triple product (p1-p0).((p2-p0)x(p3-p0)) in fp64 (:50-65; a deliberate deviation from
+//                   the reference's float32 torch.det, whose LU sign is backend dependent on numerically
+//                   degenerate tets: the two agree wherever |det| is above rounding noise, which the tests
+//                   assert for their inputs with oracle/mt.py::orientation_margin), in-place swap of
 //                   columns 0/1 of negatively oriented tets (:148), occupancy code sdf>0 (:151-154)
 //                   -> 1 byte per tet, plus the totals the host needs to size the outputs.
 //   k_mt_compact    reads the code bytes only; a decoupled look-back scan places every valid tet
@@ -57,6 +60,7 @@ constexpr uint32_t kEdgeB = (1u << 0) | (2u << 2) | (3u << 4) | (2u << 6) | (3u 
 
 struct ClassifyCounters {  // lives in the 64 bytes after codes[T]
     unsigned long long n1, n2, ne;
+    unsigned long long bad;  // tets naming a point outside [0, P): the reference's indexing asserts on those
 };
 
 struct MtHeader {
@@ -72,7 +76,7 @@ __device__ __forceinline__ uint64_t make_key(int64_t a, int64_t b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restrict__ pts, int64_t *tets, int64_t T,
+__global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restrict__ pts, int64_t P, int64_t *tets, int64_t T,
                                                           const float *__restrict__ sdf, uint8_t *__restrict__ codes,
                                                           ClassifyCounters *counters) {
     unsigned long long n1 = 0, n2 = 0;
@@ -80,6 +84,13 @@ __global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restric
     auto one = [&](int64_t t, longlong2 lo, longlong2 hi) {
         int64_t i0 = lo.x, i1 = lo.y;
         const int64_t i2 = hi.x, i3 = hi.y;
+        // an index outside [0, P) would read out of bounds (the reference's torch indexing raises a device-side
+        // assert): the tet is dropped and the call fails with P3D_ERR_INVALID
+        if ((uint64_t)i0 >= (uint64_t)P || (uint64_t)i1 >= (uint64_t)P || (uint64_t)i2 >= (uint64_t)P || (uint64_t)i3 >= (uint64_t)P) {
+            codes[t] = 0;
+            atomicAdd(&counters->bad, 1ull);
+            return;
+        }
         const double p0x = __ldg(pts + 3 * i0), p0y = __ldg(pts + 3 * i0 + 1), p0z = __ldg(pts + 3 * i0 + 2);
         const double ax = __ldg(pts + 3 * i1) - p0x, ay = __ldg(pts + 3 * i1 + 1) - p0y, az = __ldg(pts + 3 * i1 + 2) - p0z;
         const double bx = __ldg(pts + 3 * i2) - p0x, by = __ldg(pts + 3 * i2 + 1) - p0y, bz = __ldg(pts + 3 * i2 + 2) - p0z;
@@ -530,14 +541,15 @@ p3d_status p3d_mt_classify(const float *points, int64_t num_points, int64_t *tet
     if (num_tets > 0) {
         const int64_t want = (num_tets + kThreads - 1) / kThreads;
         const int64_t cap = (int64_t)sm_count() * 16;
-        k_mt_classify<<<(unsigned)(want < cap ? want : cap), kThreads, 0, s>>>(points, tets, num_tets, sdf, codes, ctr);
+        k_mt_classify<<<(unsigned)(want < cap ? want : cap), kThreads, 0, s>>>(points, num_points, tets, num_tets, sdf, codes, ctr);
         MT_CUDA(cudaGetLastError());
     }
     int64_t *pin = mt_pinned();
     int64_t *dst = pin ? pin : counts_host;
-    MT_CUDA(cudaMemcpyAsync(dst, ctr, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MT_CUDA(cudaMemcpyAsync(dst, ctr, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MT_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 3; ++i) counts_host[i] = dst[i];
+    if (dst[3] != 0) MT_FAIL(P3D_ERR_INVALID, "p3d_mt_classify: " + std::to_string(dst[3]) + " tets name a point outside [0, num_points)");
     return P3D_OK;
 }
 

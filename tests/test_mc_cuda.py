@@ -370,6 +370,57 @@ def test_workspace_reuse_and_errors():
     assert e.value.status == capi.P3D_ERR_WORKSPACE
 
 
+@pytest.mark.parametrize("name", ["bunny66", "noise33_s0", "gyroid128", "bounds_asym", "empty"])
+def test_one_shot_c_entry_with_a_cudamalloc_callback(name):
+    """p3d_mc_run (include/prim3d_b200.h) the way a C caller uses it: no torch on the path, device memory from a
+    callback that calls cudaMalloc, results read back with cudaMemcpy."""
+    import ctypes
+    from primitive3d_b200 import capi
+    make, thresh, lower, upper = CASES[name]
+    grid = np.ascontiguousarray(make(), dtype=np.float32)
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rt.cudaFree.argtypes = [ctypes.c_void_p]
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")  # a context on device 0
+    blocks = []
+
+    @ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+    def alloc(_ctx, nbytes):
+        ptr = ctypes.c_void_p()
+        if rt.cudaMalloc(ctypes.byref(ptr), max(nbytes, 1)) != 0:
+            return None
+        blocks.append(ptr.value)
+        return ptr.value
+
+    L = capi.lib()
+    L.p3d_mc_run.restype = ctypes.c_int
+    L.p3d_mc_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]
+    try:
+        gptr = ctypes.c_void_p(alloc(None, grid.nbytes))
+        assert rt.cudaMemcpy(gptr, grid.ctypes.data, grid.nbytes, 1) == 0
+        desc = capi.McDesc.make(grid.shape, thresh, lower, upper)
+        vp, fp = ctypes.c_void_p(), ctypes.c_void_p()
+        nv, nf = ctypes.c_int64(-1), ctypes.c_int64(-1)
+        capi.check(L.p3d_mc_run(ctypes.byref(desc), gptr, ctypes.cast(alloc, ctypes.c_void_p), None, ctypes.byref(vp),
+                                ctypes.byref(fp), ctypes.byref(nv), ctypes.byref(nf), None))
+        v = np.empty((nv.value, 3), np.float32)
+        f = np.empty((nf.value, 3), np.int32)
+        if v.size:
+            assert rt.cudaMemcpy(v.ctypes.data, vp, v.nbytes, 2) == 0
+        if f.size:
+            assert rt.cudaMemcpy(f.ctypes.data, fp, f.nbytes, 2) == 0
+    finally:
+        for b in blocks:
+            rt.cudaFree(ctypes.c_void_p(b))
+    ov, of = mc.marching_cubes(grid, thresh, lower, upper)
+    assert v.shape == ov.shape and f.shape == of.shape
+    assert_same_mesh(v, f, ov, of, ordered_faces=True)
+
+
 @pytest.mark.parametrize("name", ["noise33_s0", "gyroid128", "noise_long_rows", "bounds_asym"])
 def test_vertex_capacity_paths_agree(name):
     """The speculative vertex buffer of the counting pass, a too-small one (vertices-only second pass) and

@@ -99,6 +99,43 @@ def test_python_entry_point_contract():
     assert v.shape == (0, 3) and f.shape == (0, 3) and ti.shape == (0,)
 
 
+def test_tet_indices_outside_the_point_set_are_an_error():
+    """The reference's torch indexing asserts on such a tet; the classify pass reports it instead of reading out
+    of bounds."""
+    from primitive3d_b200 import capi
+    g = np.load(os.path.join(HERE, "golden", "mt_fixture.npz"))
+    pts, sdf = torch.from_numpy(g["points"]).cuda(), torch.from_numpy(g["sdf"]).cuda()
+    for bad in (len(g["points"]), -1, 1 << 40):
+        tets = torch.from_numpy(g["tets"].copy()).cuda()
+        tets[len(tets) // 2, 2] = bad
+        with pytest.raises(capi.P3DError) as e:
+            capi.marching_tetrahedra(pts, tets, sdf)
+        assert e.value.status == capi.P3D_ERR_INVALID and "outside" in str(e.value)
+    v = capi.marching_tetrahedra(pts, torch.from_numpy(g["tets"].copy()).cuda(), sdf)[0]  # and the library still works
+    assert np.array_equal(v.cpu().numpy().view(np.uint32), g["verts"].view(np.uint32))
+
+
+def test_wrapper_keeps_the_input_dtype_and_tolerates_unused_verts():
+    """The reference is dtype-generic torch code (marching_tetrahedras.py:175-189): float64 in, float64 verts and
+    gradients out.  Our kernels compute in float32; values agree to float32 rounding."""
+    import prim3d
+    g = np.load(os.path.join(HERE, "golden", "mt_kuhn8_noise.npz"))
+    pts = torch.from_numpy(g["points"]).double().cuda().requires_grad_(True)
+    sdf = torch.from_numpy(g["sdf"]).double().cuda().requires_grad_(True)
+    v, f = prim3d.marching_tetrahedras(pts, torch.from_numpy(g["tets"].copy()).cuda(), sdf)
+    assert v.dtype == torch.float64 and f.dtype == torch.int64
+    assert np.array_equal(v.detach().float().cpu().numpy().view(np.uint32), g["verts"].view(np.uint32))
+    v.sum().backward()
+    assert pts.grad.dtype == torch.float64 and sdf.grad.dtype == torch.float64 and pts.grad.abs().sum() > 0
+    with pytest.raises(TypeError):
+        prim3d.marching_tetrahedras(pts.detach().long(), torch.from_numpy(g["tets"].copy()).cuda(), sdf.detach())
+    # a loss that uses another output only: backward sees grad_verts = None for verts
+    from prim3d.utility.marching_tetrahedras import _MarchingTets
+    p32 = torch.from_numpy(g["points"]).cuda().requires_grad_(True)
+    s32 = torch.from_numpy(g["sdf"]).cuda().requires_grad_(True)
+    assert _MarchingTets.backward(type("C", (), {"saved_tensors": (p32, s32, None)})(), None, None, None, None) == (None, None, None)
+
+
 def test_gradients_match_torch_autograd_of_the_reference_formula():
     """The reference's verts are differentiable w.r.t. vertices and sdf
     (marching_tetrahedras.py:175-189); compare our backward with autograd on that formula."""

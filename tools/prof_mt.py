@@ -1,14 +1,32 @@
-import sys, torch, time
+"""Times prim3d.marching_tetrahedras on the Kuhn grid (BASELINE configs[3] at n = 128).
+  python tools/prof_mt.py [n] [calls]      calls = 0: ONE call, for an ncu capture"""
+import sys
+import time
+
+import torch
+
 sys.path.insert(0, '.')
-import prim3d
-from primitive3d_b200 import workloads as inputs
-pts, tets, sdf = inputs.kuhn_tet_grid(128)
+import prim3d  # noqa: E402
+from primitive3d_b200 import workloads as inputs  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+calls = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+pts, tets, sdf = inputs.kuhn_tet_grid(n)
 P, T, S = torch.from_numpy(pts).cuda(), torch.from_numpy(tets).cuda(), torch.from_numpy(sdf).cuda()
-for _ in range(3):
+if calls == 0:
     v, f = prim3d.marching_tetrahedras(P, T.clone(), S)
+    torch.cuda.synchronize()
+    print(v.shape, f.shape)
+    sys.exit(0)
+clones = [T.clone() for _ in range(calls + 3)]
+for i in range(3):
+    v, f = prim3d.marching_tetrahedras(P, clones[i], S)
 torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 t = time.perf_counter()
-for _ in range(10):
-    v, f = prim3d.marching_tetrahedras(P, T.clone(), S)
+ev[0].record()
+for i in range(calls):
+    v, f = prim3d.marching_tetrahedras(P, clones[3 + i], S)
+ev[1].record()
 torch.cuda.synchronize()
-print("ms per call incl clone", (time.perf_counter() - t) / 10 * 1e3, v.shape, f.shape)
+print("ms per call: wall %.4f, device %.4f" % ((time.perf_counter() - t) / calls * 1e3, ev[0].elapsed_time(ev[1]) / calls), tuple(v.shape), tuple(f.shape))
