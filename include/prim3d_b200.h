@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 3
+#define P3D_ABI_VERSION 4
 
 typedef enum p3d_status {
     P3D_OK = 0,
@@ -286,8 +286,11 @@ p3d_status p3d_mc_run(const p3d_mc_desc *desc, const float *grid, p3d_alloc_fn a
 /* Bytes of the device buffer `codes` (one byte per tet plus the classify counters). */
 size_t p3d_mt_codes_bytes(int64_t num_tets);
 
+/* oriented: 0 = fix the orientation of `tets` in place; 1 = they went through this library before
+ * (see p3d_mt_extract). */
 p3d_status p3d_mt_classify(const float *points, int64_t num_points, int64_t *tets, int64_t num_tets,
-                           const float *sdf, uint8_t *codes, int64_t *counts_host, void *stream);
+                           const float *sdf, int oriented, uint8_t *codes, int64_t *counts_host,
+                           void *stream);
 
 /* Bytes of device workspace p3d_mt_index / p3d_mt_emit need, from p3d_mt_classify's counts. */
 size_t p3d_mt_workspace_bytes(int64_t num_tets, int64_t n1, int64_t n2, int64_t ne);
@@ -301,6 +304,45 @@ p3d_status p3d_mt_emit(const float *points, const int64_t *tets, int64_t num_tet
                        const uint8_t *codes, int64_t n1, int64_t n2, int64_t ne, int64_t num_vertices,
                        const void *workspace, float *verts, int64_t *edges, int64_t *faces,
                        int64_t *tet_idx, void *stream);
+
+/* The whole of marching tetrahedra in ONE call with one host synchronisation (three launches), for the
+ * case the path exists for: an isosurface that cuts a small part of the tets (valid tets and crossing-edge
+ * instances in the thousands to low millions).  Same outputs as classify + index + emit.
+ *
+ * Every capacity is the caller's guess (the previous call's counts plus a margin; anything for the first
+ * call): the kernels count everything, write only what fits, and counts_host says what happened:
+ *   counts_host[0..3] = {n1, n2, ne, V}   (F = n1 + 2*n2);
+ *   counts_host[4]    = 0  outputs complete;
+ *                       1  an output capacity was too small (slot_capacity < max(n1, n2),
+ *                          vertex_capacity < V or face_capacity < F): call again with capacities from
+ *                          the counts and oriented = 1;
+ *                       2  a bucket overflowed: {n1, n2, ne} are valid, V is not (V <= ne).  If n1 + n2 is
+ *                          above the slot_capacity passed or ne above the key_capacity passed, the buckets
+ *                          were sized for too few entries: call again with slot_capacity = n1 + n2,
+ *                          key_capacity = ne and oriented = 1.  Otherwise the ids are crowded into few
+ *                          buckets: use the staged calls above (oriented = 1), which sort with the general
+ *                          radix sort;
+ *                       3  nothing was run: more than ~2 M valid tets or ~8 M crossing edges expected
+ *                          (slot_capacity / key_capacity): use the staged calls.
+ *   oriented         0: fix the orientation of `tets` in place (the reference's behaviour);
+ *                    1: `tets` went through a call of this library before (state 1 or 2 above): leave
+ *                       them alone.  Fixing twice is NOT the same as fixing once for a tet whose volume
+ *                       is within rounding of zero, and the reference fixes once;
+ *   slot_capacity    valid tets expected (sizes the slot buckets), and the capacity of each of the two
+ *                    scratch lists (one-triangle / two-triangle tets);
+ *   key_capacity     crossing-edge instances expected: sizes the key buckets (it bounds nothing else);
+ *   verts float[3*vertex_capacity], edges int64[2*vertex_capacity] or NULL,
+ *   faces int64[3*face_capacity], tet_idx int64[face_capacity] or NULL;
+ *   workspace        p3d_mt_extract_workspace_bytes(...) bytes of device memory, 256-byte aligned.
+ * A tet naming a point outside [0, num_points) fails the call with P3D_ERR_INVALID (the reference's
+ * indexing raises a device-side assert there). */
+size_t p3d_mt_extract_workspace_bytes(int64_t num_tets, int64_t num_points, int64_t slot_capacity,
+                                      int64_t key_capacity);
+p3d_status p3d_mt_extract(const float *points, int64_t num_points, int64_t *tets, int64_t num_tets,
+                          const float *sdf, int oriented, void *workspace, size_t workspace_bytes,
+                          int64_t slot_capacity, int64_t key_capacity, float *verts, int64_t *edges,
+                          int64_t vertex_capacity, int64_t *faces, int64_t *tet_idx,
+                          int64_t face_capacity, int64_t *counts_host, void *stream);
 
 /* Backward of the vertex interpolation (the reference's verts are differentiable w.r.t.
  * points and sdf, marching_tetrahedras.py:175-189): accumulates into grad_points [P,3] and

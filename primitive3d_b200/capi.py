@@ -105,13 +105,17 @@ def _bind_mt(L, vp, i64, sz):
     L.p3d_mt_codes_bytes.restype = sz
     L.p3d_mt_codes_bytes.argtypes = [i64]
     L.p3d_mt_classify.restype = ctypes.c_int
-    L.p3d_mt_classify.argtypes = [vp, i64, vp, i64, vp, vp, pi64, vp]
+    L.p3d_mt_classify.argtypes = [vp, i64, vp, i64, vp, ctypes.c_int, vp, pi64, vp]
     L.p3d_mt_workspace_bytes.restype = sz
     L.p3d_mt_workspace_bytes.argtypes = [i64, i64, i64, i64]
     L.p3d_mt_index.restype = ctypes.c_int
     L.p3d_mt_index.argtypes = [vp, i64, i64, vp, vp, i64, i64, i64, vp, sz, pi64, vp]
     L.p3d_mt_emit.restype = ctypes.c_int
     L.p3d_mt_emit.argtypes = [vp, vp, i64, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp]
+    L.p3d_mt_extract_workspace_bytes.restype = sz
+    L.p3d_mt_extract_workspace_bytes.argtypes = [i64, i64, i64, i64]
+    L.p3d_mt_extract.restype = ctypes.c_int
+    L.p3d_mt_extract.argtypes = [vp, i64, vp, i64, vp, ctypes.c_int, vp, sz, i64, i64, vp, vp, i64, vp, vp, i64, pi64, vp]
     L.p3d_mt_backward.restype = ctypes.c_int
     L.p3d_mt_backward.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
 
@@ -350,20 +354,51 @@ def marching_cubes(grid, thresh, lower=None, upper=None, vertex_capacity=None):
     return mc_vertices(desc, grid, ws, V, vbuf), mc_faces(desc, ws, F)
 
 
-def marching_tetrahedra(points, tets, sdf):
+def marching_tetrahedra(points, tets, sdf, staged=False, capacities=None):
     """Marching tetrahedra through the C ABI: points f32 [P,3], tets i64 [T,4] (mutated in place),
     sdf f32 [P], all contiguous CUDA tensors -> (verts f32 [V,3], faces i64 [F,3], tet_idx i64 [F],
-    edges i64 [V,2])."""
+    edges i64 [V,2]).
+
+    One call of p3d_mt_extract (a second one with exact capacities if the guess `capacities` = (slot, key, vertex,
+    face) was too small); the staged calls p3d_mt_classify / p3d_mt_index / p3d_mt_emit when `staged` or when the
+    library reports that the input does not suit the one-call layout."""
     if not (points.is_cuda and tets.is_cuda and sdf.is_cuda and points.is_contiguous() and tets.is_contiguous()
             and sdf.is_contiguous() and points.dtype == torch.float32 and tets.dtype == torch.int64
             and sdf.dtype == torch.float32):
         raise ValueError("points/sdf must be contiguous float32 and tets contiguous int64 CUDA tensors")
     L, dev = lib(), points.device
     P, T = points.shape[0], tets.shape[0]
+    oriented = 0
+    if not staged:
+        slot, key, vcap, fcap = capacities if capacities is not None else (min(T, T // 16 + 4096), T // 4 + 4096, T // 4 + 4096,
+                                                                           3 * min(T, T // 16 + 4096))
+        with torch.cuda.device(dev):
+            for _ in range(2):
+                ws = torch.empty(L.p3d_mt_extract_workspace_bytes(T, P, slot, key), dtype=torch.uint8, device=dev)
+                verts = torch.empty((vcap, 3), dtype=torch.float32, device=dev)
+                edges = torch.empty((vcap, 2), dtype=torch.int64, device=dev)
+                faces = torch.empty((fcap, 3), dtype=torch.int64, device=dev)
+                tet_idx = torch.empty((fcap,), dtype=torch.int64, device=dev)
+                c = (ctypes.c_int64 * 5)()
+                check(L.p3d_mt_extract(points.data_ptr(), P, tets.data_ptr(), T, sdf.data_ptr(), oriented, ws.data_ptr(), ws.numel(),
+                                       slot, key, verts.data_ptr(), edges.data_ptr(), vcap, faces.data_ptr(), tet_idx.data_ptr(), fcap,
+                                       c, _stream()))
+                marching_tetrahedra.last_state = c[4]
+                if c[4] == 3:
+                    break        # nothing ran
+                oriented = 1     # the tets are fixed now: a later pass must not fix them again
+                # too small a guess (1), or buckets sized for fewer entries than there are (2 with counts above the
+                # guesses; V is unknown then, ne bounds it): one more run with capacities from the counts
+                if c[4] == 0 or (c[4] == 2 and c[0] + c[1] <= slot and c[2] <= key):
+                    break
+                slot, key, vcap, fcap = c[0] + c[1], c[2], (c[3] if c[4] == 1 else c[2]), c[0] + 2 * c[1]
+        if c[4] == 0:
+            V, F = c[3], c[0] + 2 * c[1]
+            return verts[:V], faces[:F], tet_idx[:F], edges[:V]
     with torch.cuda.device(dev):
         codes = torch.empty(L.p3d_mt_codes_bytes(T), dtype=torch.uint8, device=dev)
         c = (ctypes.c_int64 * 3)()
-        check(L.p3d_mt_classify(points.data_ptr(), P, tets.data_ptr(), T, sdf.data_ptr(), codes.data_ptr(), c, _stream()))
+        check(L.p3d_mt_classify(points.data_ptr(), P, tets.data_ptr(), T, sdf.data_ptr(), oriented, codes.data_ptr(), c, _stream()))
         n1, n2, ne = c[0], c[1], c[2]
         ws = torch.empty(L.p3d_mt_workspace_bytes(T, n1, n2, ne), dtype=torch.uint8, device=dev)
         v = (ctypes.c_int64 * 1)()

@@ -5,10 +5,8 @@
 // pairs, masked scatters).  Here:
 //
 //   k_mt_classify   one streaming pass over the tets (32 B each): orientation sign from the
-//                   triple product (p1-p0).((p2-p0)x(p3-p0)) in fp64 (:50-65; a deliberate deviation from
-//                   the reference's float32 torch.det, whose LU sign is backend dependent on numerically
-//                   degenerate tets: the two agree wherever |det| is above rounding noise, which the tests
-//                   assert for their inputs with oracle/mt.py::orientation_margin), in-place swap of
+//                   triple product (p1-p0).((p2-p0)x(p3-p0)) in fp64 (:50-65; mt_common.cuh says why not the
+//                   reference's float32 torch.det), in-place swap of
 //                   columns 0/1 of negatively oriented tets (:148), occupancy code sdf>0 (:151-154)
 //                   -> 1 byte per tet, plus the totals the host needs to size the outputs.
 //   k_mt_compact    reads the code bytes only; a decoupled look-back scan places every valid tet
@@ -26,6 +24,7 @@
 
 #include <string>
 
+#include "mt_common.cuh"
 #include "p3d_error.h"
 #include "scan_utils.cuh"
 
@@ -39,25 +38,6 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kThreads * kSortItems;      // radix-sort tile (4096 keys)
 constexpr int kUniqTile = kThreads * 8;
 
-// marching_tetrahedras.py:29-32 num_triangles_table, 2 bits per code
-constexpr uint32_t pack_num_tri() {
-    const int nt[16] = {0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1, 0};
-    uint32_t w = 0;
-    for (int i = 0; i < 16; ++i) w |= (uint32_t)nt[i] << (2 * i);
-    return w;
-}
-constexpr uint32_t kNumTri = pack_num_tri();
-__host__ __device__ __forceinline__ uint32_t num_tri(uint32_t code) { return (kNumTri >> (2 * code)) & 3u; }
-
-// marching_tetrahedras.py:7-27 triangle_table: six local edge ids per code, one nibble each.
-__constant__ uint32_t c_tri_rows[16] = {
-    0xffffff, 0xfff201, 0xfff304, 0x431241, 0xfff513, 0x352032, 0x451041, 0xfff524,
-    0xfff254, 0x154014, 0x253023, 0xfff531, 0x134214, 0xfff403, 0xfff102, 0xffffff};
-// marching_tetrahedras.py:33-43 base_tet_edges: local edge -> (corner a, corner b), 2 bits each
-//   e: 0:(0,1) 1:(0,2) 2:(0,3) 3:(1,2) 4:(1,3) 5:(2,3)
-constexpr uint32_t kEdgeA = (0u << 0) | (0u << 2) | (0u << 4) | (1u << 6) | (1u << 8) | (2u << 10);
-constexpr uint32_t kEdgeB = (1u << 0) | (2u << 2) | (3u << 4) | (2u << 6) | (3u << 8) | (3u << 10);
-
 struct ClassifyCounters {  // lives in the 64 bytes after codes[T]
     unsigned long long n1, n2, ne;
     unsigned long long bad;  // tets naming a point outside [0, P): the reference's indexing asserts on those
@@ -70,15 +50,10 @@ struct MtHeader {
     unsigned long long num_unique;
 };
 
-__device__ __forceinline__ uint64_t make_key(int64_t a, int64_t b) {
-    const uint64_t lo = (uint64_t)(a < b ? a : b), hi = (uint64_t)(a < b ? b : a);
-    return (lo << 32) | hi;
-}
-
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restrict__ pts, int64_t P, int64_t *tets, int64_t T,
                                                           const float *__restrict__ sdf, uint8_t *__restrict__ codes,
-                                                          ClassifyCounters *counters) {
+                                                          ClassifyCounters *counters, int oriented) {
     unsigned long long n1 = 0, n2 = 0;
     longlong2 *t2 = reinterpret_cast<longlong2 *>(tets);
     auto one = [&](int64_t t, longlong2 lo, longlong2 hi) {
@@ -91,12 +66,7 @@ __global__ void __launch_bounds__(kThreads) k_mt_classify(const float *__restric
             atomicAdd(&counters->bad, 1ull);
             return;
         }
-        const double p0x = __ldg(pts + 3 * i0), p0y = __ldg(pts + 3 * i0 + 1), p0z = __ldg(pts + 3 * i0 + 2);
-        const double ax = __ldg(pts + 3 * i1) - p0x, ay = __ldg(pts + 3 * i1 + 1) - p0y, az = __ldg(pts + 3 * i1 + 2) - p0z;
-        const double bx = __ldg(pts + 3 * i2) - p0x, by = __ldg(pts + 3 * i2 + 1) - p0y, bz = __ldg(pts + 3 * i2 + 2) - p0z;
-        const double cx = __ldg(pts + 3 * i3) - p0x, cy = __ldg(pts + 3 * i3 + 1) - p0y, cz = __ldg(pts + 3 * i3 + 2) - p0z;
-        // det([1|p0; 1|p1; 1|p2; 1|p3]) = a . (b x c)   (marching_tetrahedras.py:61-64)
-        const double det = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+        const double det = oriented ? 0.0 : orient_det_f64(pts, i0, i1, i2, i3);  // marching_tetrahedras.py:61-64
         if (det < 0.0) {  // :148 tets[flip, :2] = tets[flip][:, [1, 0]]
             const int64_t s = i0;
             i0 = i1;
@@ -386,21 +356,7 @@ __global__ void __launch_bounds__(kThreads) k_mt_verts(const float *__restrict__
                                                        float *__restrict__ verts, int64_t *__restrict__ edges) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
-    const uint64_t key = ukeys[i];
-    const int64_t a = (int64_t)(key >> 32), b = (int64_t)(key & 0xffffffffull);
-    // marching_tetrahedras.py:177-189, every op separately rounded
-    const float s0 = __ldg(sdf + a);
-    const float s1n = __fmul_rn(__ldg(sdf + b), -1.0f);  // edges_to_interp_sdf[:, -1] *= -1
-    const float den = __fadd_rn(s0, s1n);                 // .sum(1)
-    const float w0 = __fdiv_rn(s1n, den);                 // flip(...) / denominator
-    const float w1 = __fdiv_rn(s0, den);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        verts[3 * i + c] = __fadd_rn(__fmul_rn(__ldg(pts + 3 * a + c), w0), __fmul_rn(__ldg(pts + 3 * b + c), w1));
-    if (edges) {
-        edges[2 * i] = a;
-        edges[2 * i + 1] = b;
-    }
+    emit_vertex(pts, sdf, ukeys[i], i, verts, edges);
 }
 
 __device__ __forceinline__ int64_t find_key(const uint64_t *__restrict__ ukeys, int64_t V, uint64_t key) {
@@ -477,8 +433,6 @@ struct MtLayout {
     int sort_blocks;
 };
 
-inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-
 MtLayout mt_layout(int64_t T, int64_t n1, int64_t n2, int64_t ne) {
     MtLayout l;
     l.tiles_compact = (T + kTileTets - 1) / kTileTets;
@@ -503,12 +457,6 @@ int64_t *mt_pinned() {
     return buf;
 }
 
-int id_bits(int64_t num_points) {
-    int b = 1;
-    while (b < 32 && ((int64_t)1 << b) < num_points) ++b;
-    return b;
-}
-
 }  // namespace
 
 }  // namespace p3d
@@ -530,7 +478,7 @@ size_t p3d_mt_codes_bytes(int64_t num_tets) {
 }
 
 p3d_status p3d_mt_classify(const float *points, int64_t num_points, int64_t *tets, int64_t num_tets, const float *sdf,
-                           uint8_t *codes, int64_t *counts_host, void *stream) {
+                           int oriented, uint8_t *codes, int64_t *counts_host, void *stream) {
     if (num_tets < 0 || num_points < 0 || !counts_host || !codes) MT_FAIL(P3D_ERR_INVALID, "p3d_mt_classify: invalid argument");
     if (num_tets > 0 && (!points || !tets || !sdf)) MT_FAIL(P3D_ERR_INVALID, "p3d_mt_classify: null pointer");
     if (num_tets > (int64_t)INT32_MAX || num_points > ((int64_t)1 << 32)) MT_FAIL(P3D_ERR_OVERFLOW, "p3d_mt_classify: more than 2^31 tets or 2^32 points");
@@ -541,7 +489,7 @@ p3d_status p3d_mt_classify(const float *points, int64_t num_points, int64_t *tet
     if (num_tets > 0) {
         const int64_t want = (num_tets + kThreads - 1) / kThreads;
         const int64_t cap = (int64_t)sm_count() * 16;
-        k_mt_classify<<<(unsigned)(want < cap ? want : cap), kThreads, 0, s>>>(points, num_points, tets, num_tets, sdf, codes, ctr);
+        k_mt_classify<<<(unsigned)(want < cap ? want : cap), kThreads, 0, s>>>(points, num_points, tets, num_tets, sdf, codes, ctr, oriented);
         MT_CUDA(cudaGetLastError());
     }
     int64_t *pin = mt_pinned();

@@ -24,7 +24,8 @@ def test_header_declares_the_expected_entry_points():
               "p3d_mc_extract_host_arena_bytes", "p3d_mc_tile_async", "p3d_mc_exchange_words", "p3d_mc_export_exchange",
               "p3d_mc_faces_exchanged", "p3d_mc_sharded_extract", "p3d_ply_pack",
               "p3d_mc_run", "p3d_mc_plane_table_words", "p3d_mc_export_first_plane",
-              "p3d_mc_import_halo_plane", "p3d_mt_classify", "p3d_mt_index", "p3d_mt_emit", "p3d_mt_backward",
+              "p3d_mc_import_halo_plane", "p3d_mt_classify", "p3d_mt_index", "p3d_mt_emit", "p3d_mt_backward", "p3d_mt_extract",
+              "p3d_mt_extract_workspace_bytes",
               "p3d_last_error", "p3d_abi_version"]:
         assert s in syms
 
@@ -34,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/prim3d_b200.h but not exported"
-    assert capi.abi_version() == 3
+    assert capi.abi_version() == 4
 
 
 def test_workspace_size_is_a_few_bits_per_sample():
@@ -168,10 +169,10 @@ def test_save_mesh_ply_bytes(tmp_path):
 
 
 def test_marching_tets_packed_tables_match_reference_tables():
-    """The nibble-packed tables in mt_kernels.cu against the reference's tables
+    """The nibble-packed tables in mt_common.cuh against the reference's tables
     (marching_tetrahedras.py:7-43) as restated in oracle/mt.py."""
     from oracle import mt
-    text = open(os.path.join(ROOT, "primitive3d_b200/csrc/mt_kernels.cu")).read()
+    text = open(os.path.join(ROOT, "primitive3d_b200/csrc/mt_common.cuh")).read()
     rows = re.search(r"c_tri_rows\[16\] = \{(.*?)\};", text, re.S).group(1)
     rows = [int(x, 16) for x in re.findall(r"0x([0-9a-f]+)", rows)]
     assert len(rows) == 16

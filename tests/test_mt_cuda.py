@@ -18,12 +18,78 @@ ROOT = os.path.dirname(HERE)
 GOLDEN = ["kat", "fixture", "random0", "random1", "kuhn8", "kuhn8_noise"]
 
 
-def run_capi(pts, tets, sdf):
+def run_capi(pts, tets, sdf, **kw):
+    """p3d_mt_extract (one call) unless staged=True; every comparison against the oracle / goldens below runs on
+    the one-call path, and test_one_call_and_staged_paths_agree pins the staged calls to it."""
     from primitive3d_b200 import capi
     t = torch.from_numpy(tets.copy()).cuda()
-    v, f, ti, e = capi.marching_tetrahedra(torch.from_numpy(pts).cuda(), t, torch.from_numpy(sdf).cuda())
+    v, f, ti, e = capi.marching_tetrahedra(torch.from_numpy(pts).cuda(), t, torch.from_numpy(sdf).cuda(), **kw)
     torch.cuda.synchronize()
     return v.cpu().numpy(), f.cpu().numpy(), ti.cpu().numpy(), e.cpu().numpy(), t.cpu().numpy()
+
+
+def _same(a, b):
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x, y.view(np.uint32) if y.dtype == np.float32 else y)
+
+
+@pytest.mark.parametrize("name", GOLDEN + ["kuhn48", "noisy24", "noisy40"])
+def test_one_call_and_staged_paths_agree(name):
+    from primitive3d_b200 import capi
+    if name in GOLDEN:
+        g = np.load(os.path.join(HERE, "golden", f"mt_{name}.npz"))
+        pts, tets, sdf = g["points"], g["tets"], g["sdf"]
+    else:
+        pts, tets, sdf = inputs.kuhn_tet_grid(int(name[-2:]))
+        if name.startswith("noisy"):
+            sdf = np.random.default_rng(11).uniform(-1, 1, len(pts)).astype(np.float32)
+    a = run_capi(pts, tets, sdf, staged=True)
+    b = run_capi(pts, tets, sdf)
+    _same(a, b)
+    if name != "noisy40":   # 1.8 M crossing edges in 0.4 M tets: more than the guessed bucket layout takes
+        assert capi.marching_tetrahedra.last_state == 0
+    # capacities that are too small in every combination: the second, exact call completes
+    n1n2 = max(len(a[1]), 4)
+    for caps in ((1, 64, len(a[0]) + 8, len(a[1]) + 8), (n1n2, len(a[3]) * 8 + 64, 1, len(a[1]) + 8), (n1n2, len(a[3]) * 8 + 64, len(a[0]) + 8, 1),
+                 (n1n2, len(a[3]) * 8 + 64, len(a[0]), len(a[1]))):
+        _same(a, run_capi(pts, tets, sdf, capacities=caps))
+
+
+def test_crowded_buckets_fall_back_to_the_staged_sort():
+    """Every crossing edge starts at point 0 (a fan of tets around one vertex): one bucket takes all the keys, the
+    one-call path reports state 2 and the wrapper completes through the staged calls."""
+    from primitive3d_b200 import capi
+    rng = np.random.default_rng(3)
+    n = 6000
+    pts = rng.normal(size=(n, 3)).astype(np.float32)
+    pts[0] = 0
+    others = rng.integers(1, n, size=(4000, 3))
+    others = others[(others[:, 0] != others[:, 1]) & (others[:, 1] != others[:, 2]) & (others[:, 0] != others[:, 2])]
+    tets = np.concatenate([np.zeros((len(others), 1), np.int64), others], 1)
+    sdf = np.full(n, -1.0, np.float32)
+    sdf[0] = 1.0
+    v, f, ti, e, tets_after = run_capi(pts, tets, sdf, capacities=(len(tets), 256, 3 * len(tets), 3 * len(tets)))
+    assert capi.marching_tetrahedra.last_state == 2
+    o_tets = tets.copy()
+    ov, of, oti = mt.marching_tetrahedras(pts, o_tets, sdf, True)
+    assert np.array_equal(tets_after, o_tets) and np.array_equal(v.view(np.uint32), ov.view(np.uint32))
+    assert np.array_equal(f, of) and np.array_equal(ti, oti)
+
+
+def test_near_degenerate_tets_take_the_float64_orientation_test():
+    """Tets squashed to within float32 rounding of a plane: the float32 filter cannot decide, the float64 triple
+    product does, and the one-call and staged paths flip the same tets (also those of exactly zero volume)."""
+    rng = np.random.default_rng(9)
+    n = 4096
+    pts = rng.uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    pts[:, 2] = (pts[:, 0] * 0.5 + pts[:, 1] * 0.25) + rng.uniform(-1, 1, n).astype(np.float32) * np.float32(3e-7)
+    pts[: n // 4, 2] = pts[: n // 4, 0] * np.float32(0.5)     # exactly representable plane for a part of them
+    tets = rng.integers(0, n, size=(20000, 4)).astype(np.int64)
+    sdf = rng.uniform(-1, 1, n).astype(np.float32)
+    a = run_capi(pts, tets, sdf, staged=True)
+    b = run_capi(pts, tets, sdf)
+    assert 0 < (a[4] != tets).any(1).sum() < len(tets)
+    _same(a, b)
 
 
 @pytest.mark.parametrize("name", GOLDEN)
