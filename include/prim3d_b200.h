@@ -322,7 +322,7 @@ p3d_status p3d_mt_emit(const float *points, const int64_t *tets, int64_t num_tet
  *                          key_capacity = ne and oriented = 1.  Otherwise the ids are crowded into few
  *                          buckets: use the staged calls above (oriented = 1), which sort with the general
  *                          radix sort;
- *                       3  nothing was run: more than ~2 M valid tets or ~8 M crossing edges expected
+ *                       3  nothing was run: more than ~1 M valid tets or ~4 M crossing edges expected
  *                          (slot_capacity / key_capacity): use the staged calls.
  *   oriented         0: fix the orientation of `tets` in place (the reference's behaviour);
  *                    1: `tets` went through a call of this library before (state 1 or 2 above): leave

@@ -1,4 +1,4 @@
-// primitive3d_b200/csrc/mt_extract.cu -- marching tetrahedra in ONE call, three launches, one host
+// primitive3d_b200/csrc/mt_extract.cu -- marching tetrahedra in ONE call, four launches, one host
 // synchronisation (p3d_mt_extract, include/prim3d_b200.h).
 //
 // Same outputs as the staged calls of mt_kernels.cu (and as the reference,
@@ -16,13 +16,14 @@
 //                   bucket of its id, each of its crossing edges, a 64-bit key (min id << 32 | max id), to
 //                   the key bucket of its min id.  A bucket is a fixed-capacity region; the bucket index is
 //                   the id scaled onto the bucket count, monotone in the id.
-//   k_mtx_buckets   one CTA per bucket: bitonic sort of the bucket in shared memory, then every bucket
-//                   publishes its count and sums the counts of ALL buckets before it (each thread polls its
-//                   share: one step, not a chain), which gives
+//   k_mtx_sort      one CTA per bucket: the bucket is sorted in shared memory (by counting ranks, which also
+//                   drops duplicates, up to 512 entries; a bitonic network above), written back compacted,
+//                   counted; the counts are also summed per group of 64 buckets.
+//   k_mtx_emit      one CTA per bucket: the counts of all buckets before it (whole groups, then its own
+//                   group: one load per thread) number its entries globally, which gives
 //                     key buckets   the global number of each unique key -- bucket order then key order IS
 //                                   the lexicographic order torch.unique(dim=0) defines (:157-173) -- whose
-//                                   vertex is interpolated and written on the spot (:177-189); the unique
-//                                   keys stay, compacted, at the front of their bucket;
+//                                   vertex is interpolated and written (:177-189);
 //                     slot buckets  each valid tet's place in the reference's face order: all one-triangle
 //                                   tets, then all two-triangle tets, each group in tet order (:205-223).
 //   k_mtx_faces     per face slot: the tet's table row (:193-223), each edge's vertex id = unique base of
@@ -46,19 +47,21 @@ namespace p3d {
 namespace {
 
 constexpr int kXThreads = 256;
-constexpr int kBucketCap = 4096;                // entries per bucket (32 KB of shared memory when sorted)
-constexpr int kBucketMean = 512;                // buckets are sized for this many entries on average
-constexpr int kMaxKeyBucketBits = 12;           // at most 4096 key buckets (128 MB of bucket regions)
-constexpr int kMaxSlotBucketBits = 10;          // at most 1024 slot buckets
-constexpr int kSortThreads = 256;
-constexpr unsigned long long kReady = 1ull << 62;
+constexpr int kBucketCap = 2048;                // entries per bucket (16 KB each in global memory)
+constexpr int kBucketMean = 128;                // buckets are sized for this many entries on average
+constexpr int kMaxKeyBucketBits = 13;           // at most 8192 key buckets (64 MB of bucket regions)
+constexpr int kMaxSlotBucketBits = 11;          // at most 2048 slot buckets
+constexpr int kSortThreads = 128;
+constexpr int kRankSortMax = 512;               // up to here a bucket is sorted by counting, above by a bitonic network
+constexpr int kGroup = 64;                      // buckets per group of the two-level sum of the bucket counts
+constexpr uint64_t kHole = ~0ull;               // no key and no slot entry has this value
 
 // Bucket of an id in [0, N): the id scaled onto [0, num_buckets), monotone in the id, so bucket order then
 // entry order is entry order.  scale = floor(num_buckets * 2^32 / N).
 __device__ __forceinline__ uint32_t bucket_of(uint64_t id, uint64_t scale) { return (uint32_t)((id * scale) >> 32); }
 
 struct XHeader {
-    unsigned int ticket;              // bucket jobs handed out
+    unsigned int pad;
     unsigned int overflow;            // a bucket received more than kBucketCap entries
     unsigned long long n1, n2, ne;    // one-triangle tets, two-triangle tets, crossing-edge instances
     unsigned long long bad;           // tets naming a point outside [0, P)
@@ -68,7 +71,8 @@ struct XHeader {
 struct XBuckets {   // one class of buckets (slots or keys)
     uint32_t *cursors;
     uint64_t *regions;
-    unsigned long long *status;
+    unsigned long long *counts;      // per bucket, once sorted: unique keys, or one- | two-triangle tets << 31
+    unsigned long long *group_sum;   // per group of kGroup buckets: the sum of their counts
     uint64_t scale;
     int count;
 };
@@ -192,117 +196,180 @@ __device__ __forceinline__ unsigned long long cta_excl_scan64(unsigned long long
     return lower + incl - v;
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-k_mtx_buckets(const float *__restrict__ pts, const float *__restrict__ sdf, XHeader *hdr, XBuckets slots, XBuckets keys,
-              uint32_t *__restrict__ ubase, float *__restrict__ verts, int64_t *__restrict__ edges, int64_t vcap,
-              uint64_t *__restrict__ list1, uint64_t *__restrict__ list2, int64_t slot_cap) {
-    __shared__ uint64_t s_key[kBucketCap];
-    __shared__ unsigned long long s_warp[kSortThreads / 32];
-    __shared__ unsigned int s_job;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kPerMax = kBucketCap / kSortThreads;  // 16
-    for (;;) {
-        if (threadIdx.x == 0) s_job = atomicAdd(&hdr->ticket, 1u);
-        __syncthreads();
-        const int job = (int)s_job;
-        if (job >= slots.count + keys.count) break;
-        const bool is_key = job >= slots.count;
-        const XBuckets &cls = is_key ? keys : slots;
-        const int b = is_key ? job - slots.count : job;
-        uint32_t n = cls.cursors[b];
-        if (n > (uint32_t)kBucketCap) {  // reported; the bucket is skipped and the caller takes another path
-            if (threadIdx.x == 0) hdr->overflow = 1u;
-            n = 0;
-        }
-        if (is_key && threadIdx.x == 0 && cls.cursors[b]) atomicAdd(&hdr->ne, (unsigned long long)cls.cursors[b]);
-        uint64_t *region = cls.regions + (size_t)b * kBucketCap;
-        uint32_t n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        uint32_t flags = 0, i0 = 0;
-        unsigned long long mine = 0;
-        if (n > 0) {
-            for (uint32_t i = threadIdx.x; i < n2; i += kSortThreads) s_key[i] = i < n ? region[i] : ~0ull;
-            __syncthreads();
-            for (uint32_t k = 2; k <= n2; k <<= 1)
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = threadIdx.x; i < n2 / 2; i += kSortThreads) {
-                        const uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l + j;
-                        const uint64_t x = s_key[l], y = s_key[r];
-                        if ((x > y) == ((l & k) == 0u)) {
-                            s_key[l] = y;
-                            s_key[r] = x;
-                        }
-                    }
-                    __syncthreads();
-                }
-            // a contiguous run of entries per thread.  keys: first occurrences; slots: all (ids are distinct), by kind
-            const uint32_t per = (n2 + kSortThreads - 1) / kSortThreads;
-            i0 = threadIdx.x * per;
-            for (uint32_t j = 0; j < (uint32_t)kPerMax; ++j) {
-                const uint32_t i = i0 + j;
-                if (j >= per || i >= n) break;
-                if (is_key) {
-                    if (i == 0 || s_key[i] != s_key[i - 1]) flags |= 1u << j, ++mine;
-                } else {
-                    const uint32_t nt = num_tri((uint32_t)s_key[i] & 15u);
-                    flags |= (nt == 2u ? 1u : 0u) << j;  // slots: the flag says "two triangles"
-                    mine += nt == 1u ? 1ull : (1ull << 31);
-                }
-            }
-        }
-        unsigned long long agg;
-        const unsigned long long excl = cta_excl_scan64(mine, s_warp, &agg);
-        // publish this bucket's count, then sum the counts of every bucket before it, each thread its share
-        if (threadIdx.x == 0) reinterpret_cast<volatile unsigned long long *>(cls.status)[b] = kReady | agg;
-        unsigned long long before = 0;
-        for (int i = threadIdx.x; i < b; i += kSortThreads) {
-            unsigned long long s;
-            do {
-                s = reinterpret_cast<volatile unsigned long long *>(cls.status)[i];
-            } while ((s & kReady) == 0ull);
-            before += s & (kReady - 1);
-        }
-        before = warp_sum64(before);
-        if (lane == 0) s_warp[warp] = before;
-        __syncthreads();
-        before = 0;
+// Sort by counting: entry i goes to slot #{j : key[j] < key[i]}.  Equal keys land on the same slot (they are
+// the same value) and leave holes behind them, which is the de-duplication.  Q entries per thread; s_in is
+// padded with kHole to an even count.
+template <int Q>
+__device__ __forceinline__ void rank_sort(const uint64_t *s_in, uint64_t *s_out, uint32_t n) {
+    uint64_t mine[Q];
+    uint32_t rank[Q];
 #pragma unroll
-        for (int w = 0; w < kSortThreads / 32; ++w) before += s_warp[w];
-        if (is_key) {
-            if (threadIdx.x == 0) {
-                ubase[b] = (uint32_t)before;
-                if (b == keys.count - 1) {
-                    ubase[keys.count] = (uint32_t)(before + agg);
-                    hdr->num_unique = before + agg;
+    for (int q = 0; q < Q; ++q) {
+        const uint32_t i = threadIdx.x + q * kSortThreads;
+        mine[q] = i < n ? s_in[i] : 0ull;
+        rank[q] = 0;
+    }
+    for (uint32_t j = 0; j < n; j += 2) {
+        const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(s_in + j);  // one broadcast load for the warp
+#pragma unroll
+        for (int q = 0; q < Q; ++q) rank[q] += (k.x < mine[q] ? 1u : 0u) + (k.y < mine[q] ? 1u : 0u);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+        if (threadIdx.x + q * kSortThreads < n) s_out[rank[q]] = mine[q];
+}
+
+// One CTA per bucket (slot buckets first, then key buckets): sorted and de-duplicated in shared memory, written back
+// to the front of the bucket's region, counted.
+__global__ void __launch_bounds__(kSortThreads)
+k_mtx_sort(XHeader *hdr, XBuckets slots, XBuckets keys) {
+    __shared__ __align__(16) uint64_t s_key[kBucketCap];
+    __shared__ uint64_t s_out[kRankSortMax];
+    __shared__ unsigned long long s_warp[kSortThreads / 32];
+    const int job = blockIdx.x;
+    const bool is_key = job >= slots.count;
+    const XBuckets &cls = is_key ? keys : slots;
+    const int b = is_key ? job - slots.count : job;
+    const uint32_t filled = cls.cursors[b];
+    uint32_t n = filled;
+    if (n > (uint32_t)kBucketCap) {  // reported; the bucket is skipped and the caller takes another path
+        if (threadIdx.x == 0) hdr->overflow = 1u;
+        n = 0;
+    }
+    if (n == 0) {
+        if (threadIdx.x == 0) cls.counts[b] = 0ull;
+        return;
+    }
+    if (is_key && threadIdx.x == 0) atomicAdd(&hdr->ne, (unsigned long long)filled);
+    uint64_t *region = cls.regions + (size_t)b * kBucketCap;
+    uint32_t n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < n2; i += kSortThreads) s_key[i] = i < n ? region[i] : kHole;
+    uint64_t *sorted = s_key;  // sorted entries with holes where duplicates were
+    if (n <= (uint32_t)kRankSortMax) {
+        for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) s_out[i] = kHole;
+        __syncthreads();
+        if (n <= kSortThreads) rank_sort<1>(s_key, s_out, n);
+        else if (n <= 2 * kSortThreads) rank_sort<2>(s_key, s_out, n);
+        else rank_sort<kRankSortMax / kSortThreads>(s_key, s_out, n);
+        sorted = s_out;
+        __syncthreads();
+    } else {
+        __syncthreads();
+        for (uint32_t k = 2; k <= n2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < n2 / 2; i += kSortThreads) {
+                    const uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l + j;
+                    const uint64_t x = s_key[l], y = s_key[r];
+                    if ((x > y) == ((l & k) == 0u)) {
+                        s_key[l] = y;
+                        s_key[r] = x;
+                    }
                 }
+                __syncthreads();
             }
-            uint32_t r = (uint32_t)excl;
-            for (uint32_t j = 0; j < (uint32_t)kPerMax; ++j)
-                if (flags & (1u << j)) {
-                    const uint64_t key = s_key[i0 + j];
-                    region[r] = key;  // unique keys, compacted at the front of the bucket's region
-                    const int64_t v = (int64_t)(before + r);
-                    if (v < vcap) emit_vertex(pts, sdf, key, v, verts, edges);
-                    ++r;
-                }
-        } else if (n > 0) {
-            const unsigned long long pos = before + excl;
-            int64_t p1 = (int64_t)(pos & 0x7fffffffull), p2 = (int64_t)(pos >> 31);
-            const uint32_t per = (n2 + kSortThreads - 1) / kSortThreads;
-            for (uint32_t j = 0; j < (uint32_t)kPerMax; ++j) {
-                const uint32_t i = i0 + j;
-                if (j >= per || i >= n) break;
-                const uint64_t entry = ((s_key[i] >> 4) & 0xffffffffull) | ((s_key[i] & 15ull) << 32);  // tet | code << 32
-                if (flags & (1u << j)) {
-                    if (p2 < slot_cap) list2[p2] = entry;
-                    ++p2;
-                } else {
-                    if (p1 < slot_cap) list1[p1] = entry;
-                    ++p1;
-                }
-            }
+        bool dup[kBucketCap / kSortThreads];
+#pragma unroll
+        for (int q = 0; q < kBucketCap / kSortThreads; ++q) {
+            const uint32_t i = threadIdx.x + q * kSortThreads;
+            dup[q] = i > 0 && i < n && s_key[i] == s_key[i - 1];
         }
         __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kBucketCap / kSortThreads; ++q)
+            if (dup[q]) s_key[threadIdx.x + q * kSortThreads] = kHole;
+        __syncthreads();
+    }
+    // a contiguous run of sorted entries per thread; the survivors go back to the front of the region, in order
+    const uint32_t per = (n + kSortThreads - 1) / kSortThreads;
+    const uint32_t i0 = threadIdx.x * per;
+    unsigned long long mine = 0, kinds = 0;
+    for (uint32_t j = 0; j < per; ++j) {
+        const uint32_t i = i0 + j;
+        if (i >= n) break;
+        const uint64_t e = sorted[i];
+        if (e == kHole) continue;
+        ++mine;
+        if (!is_key) kinds += num_tri((uint32_t)e & 15u) == 1u ? 1ull : (1ull << 31);
+    }
+    unsigned long long agg, kagg = 0;
+    const unsigned long long excl = cta_excl_scan64(mine, s_warp, &agg);
+    if (!is_key) cta_excl_scan64(kinds, s_warp, &kagg);
+    uint32_t r = (uint32_t)excl;
+    for (uint32_t j = 0; j < per; ++j) {
+        const uint32_t i = i0 + j;
+        if (i >= n) break;
+        const uint64_t e = sorted[i];
+        if (e != kHole) region[r++] = e;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long c = is_key ? agg : kagg;
+        cls.counts[b] = c;
+        atomicAdd(cls.group_sum + b / kGroup, c);
+    }
+}
+
+// One CTA per bucket again, now that every count is known: the sum of the counts before the bucket (whole groups,
+// then the buckets of its own group) numbers its entries globally.  Key buckets write their vertices, slot buckets
+// place their tets in the two face-order lists.
+__global__ void __launch_bounds__(kSortThreads)
+k_mtx_emit(const float *__restrict__ pts, const float *__restrict__ sdf, XHeader *hdr, XBuckets slots, XBuckets keys,
+           uint32_t *__restrict__ ubase, float *__restrict__ verts, int64_t *__restrict__ edges, int64_t vcap,
+           uint64_t *__restrict__ list1, uint64_t *__restrict__ list2, int64_t slot_cap) {
+    __shared__ unsigned long long s_warp[kSortThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int job = blockIdx.x;
+    const bool is_key = job >= slots.count;
+    const XBuckets &cls = is_key ? keys : slots;
+    const int b = is_key ? job - slots.count : job;
+    const int g = b / kGroup;
+    static_assert(kSortThreads >= kGroup && (1 << kMaxKeyBucketBits) / kGroup <= kSortThreads, "one load per thread");
+    unsigned long long before = (int)threadIdx.x < g ? cls.group_sum[threadIdx.x] : 0ull;
+    if (g * kGroup + (int)threadIdx.x < b) before += cls.counts[g * kGroup + threadIdx.x];
+    const unsigned long long count = cls.counts[b];
+    before = warp_sum64(before);
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
+    before = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) before += s_warp[w];
+    __syncthreads();
+    const uint64_t *region = cls.regions + (size_t)b * kBucketCap;
+    if (is_key) {
+        if (threadIdx.x == 0) {
+            ubase[b] = (uint32_t)before;
+            if (b == keys.count - 1) {
+                ubase[keys.count] = (uint32_t)(before + count);
+                hdr->num_unique = before + count;
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < (uint32_t)count; i += kSortThreads) {
+            const int64_t v = (int64_t)(before + i);
+            if (v < vcap) emit_vertex(pts, sdf, region[i], v, verts, edges);
+        }
+    } else {
+        const uint32_t n = (uint32_t)(count & 0x7fffffffull) + (uint32_t)(count >> 31);
+        if (n == 0) return;
+        const uint32_t per = (n + kSortThreads - 1) / kSortThreads;
+        const uint32_t i0 = threadIdx.x * per;
+        unsigned long long kinds = 0;
+        for (uint32_t j = 0; j < per; ++j)
+            if (i0 + j < n) kinds += num_tri((uint32_t)region[i0 + j] & 15u) == 1u ? 1ull : (1ull << 31);
+        unsigned long long kagg;
+        const unsigned long long pos = before + cta_excl_scan64(kinds, s_warp, &kagg);
+        int64_t p1 = (int64_t)(pos & 0x7fffffffull), p2 = (int64_t)(pos >> 31);
+        for (uint32_t j = 0; j < per; ++j) {
+            if (i0 + j >= n) break;
+            const uint64_t e = region[i0 + j];
+            const uint64_t entry = ((e >> 4) & 0xffffffffull) | ((e & 15ull) << 32);  // tet | code << 32
+            if (num_tri((uint32_t)e & 15u) == 2u) {
+                if (p2 < slot_cap) list2[p2] = entry;
+                ++p2;
+            } else {
+                if (p1 < slot_cap) list1[p1] = entry;
+                ++p1;
+            }
+        }
     }
 }
 
@@ -357,7 +424,7 @@ k_mtx_faces(const int64_t *__restrict__ tets, const XHeader *__restrict__ hdr, c
 }
 
 struct XLayout {
-    size_t header, status_slots, status_keys, cursors_slots, cursors_keys, zeroed, ubase, list1, list2, regions_slots, regions_keys, total;
+    size_t header, cursors_slots, cursors_keys, groups_slots, groups_keys, zeroed, counts_slots, counts_keys, ubase, list1, list2, regions_slots, regions_keys, total;
     int slot_buckets, key_buckets;
     uint64_t slot_scale, key_scale;
 };
@@ -377,19 +444,22 @@ bool x_layout(int64_t T, int64_t P, int64_t slot_cap, int64_t key_cap, XLayout *
     l->key_scale = P > 0 ? (((uint64_t)l->key_buckets << 32) / (uint64_t)P) : 0;
     size_t off = 0;
     l->header = off;        off += up256(sizeof(XHeader));
-    l->status_slots = off;  off += up256((size_t)l->slot_buckets * 8);
-    l->status_keys = off;   off += up256((size_t)l->key_buckets * 8);
     l->cursors_slots = off; off += up256((size_t)l->slot_buckets * 4);
     l->cursors_keys = off;  off += up256((size_t)l->key_buckets * 4);
+    l->groups_slots = off;  off += up256((size_t)(l->slot_buckets / kGroup + 1) * 8);
+    l->groups_keys = off;   off += up256((size_t)(l->key_buckets / kGroup + 1) * 8);
     l->zeroed = off;
+    l->counts_slots = off;  off += up256((size_t)l->slot_buckets * 8);
+    l->counts_keys = off;   off += up256((size_t)l->key_buckets * 8);
     l->ubase = off;         off += up256((size_t)(l->key_buckets + 1) * 4);
     l->list1 = off;         off += up256((size_t)slot_cap * 8);
     l->list2 = off;         off += up256((size_t)slot_cap * 8);
     l->regions_slots = off; off += (size_t)l->slot_buckets * kBucketCap * 8;
     l->regions_keys = off;  off += (size_t)l->key_buckets * kBucketCap * 8;
     l->total = off;
-    // an average bucket more than half full will overflow somewhere: such inputs belong to the staged path
-    return key_cap <= (int64_t)l->key_buckets * (kBucketCap / 2) && slot_cap <= (int64_t)l->slot_buckets * (kBucketCap / 2);
+    // more entries expected than the largest layout takes at a quarter of its capacity: such inputs belong to the
+    // staged path (fewer buckets because there are few ids is no reason: a bucket that overflows says so itself)
+    return key_cap <= ((int64_t)(kBucketCap / 4) << kMaxKeyBucketBits) && slot_cap <= ((int64_t)(kBucketCap / 4) << kMaxSlotBucketBits);
 }
 
 int64_t *x_pinned() {
@@ -445,12 +515,14 @@ p3d_status p3d_mt_extract(const float *points, int64_t num_points, int64_t *tets
     XBuckets slots, keys;
     slots.cursors = reinterpret_cast<uint32_t *>(base + l.cursors_slots);
     slots.regions = reinterpret_cast<uint64_t *>(base + l.regions_slots);
-    slots.status = reinterpret_cast<unsigned long long *>(base + l.status_slots);
+    slots.counts = reinterpret_cast<unsigned long long *>(base + l.counts_slots);
+    slots.group_sum = reinterpret_cast<unsigned long long *>(base + l.groups_slots);
     slots.scale = l.slot_scale;
     slots.count = l.slot_buckets;
     keys.cursors = reinterpret_cast<uint32_t *>(base + l.cursors_keys);
     keys.regions = reinterpret_cast<uint64_t *>(base + l.regions_keys);
-    keys.status = reinterpret_cast<unsigned long long *>(base + l.status_keys);
+    keys.counts = reinterpret_cast<unsigned long long *>(base + l.counts_keys);
+    keys.group_sum = reinterpret_cast<unsigned long long *>(base + l.groups_keys);
     keys.scale = l.key_scale;
     keys.count = l.key_buckets;
     uint32_t *ubase = reinterpret_cast<uint32_t *>(base + l.ubase);
@@ -465,11 +537,9 @@ p3d_status p3d_mt_extract(const float *points, int64_t num_points, int64_t *tets
         k_mtx_classify<<<(unsigned)(want < cap ? want : cap), kXThreads, 0, s>>>(points, (uint32_t)num_points, tets, num_tets, sdf, hdr,
                                                                               slots, keys, oriented);
     }
-    {
-        const int jobs = l.slot_buckets + l.key_buckets, cap = sms * 6;
-        k_mtx_buckets<<<jobs < cap ? jobs : cap, kSortThreads, 0, s>>>(points, sdf, hdr, slots, keys, ubase, verts, edges, vertex_capacity,
-                                                                      list1, list2, slot_capacity);
-    }
+    const int jobs = l.slot_buckets + l.key_buckets;
+    k_mtx_sort<<<jobs, kSortThreads, 0, s>>>(hdr, slots, keys);
+    k_mtx_emit<<<jobs, kSortThreads, 0, s>>>(points, sdf, hdr, slots, keys, ubase, verts, edges, vertex_capacity, list1, list2, slot_capacity);
     if (face_capacity > 0)
         k_mtx_faces<<<(unsigned)((face_capacity + kXThreads - 1) / kXThreads), kXThreads, 0, s>>>(
             tets, hdr, list1, list2, slot_capacity, keys.regions, ubase, keys.scale, face_capacity, faces, tet_idx);
