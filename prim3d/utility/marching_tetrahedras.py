@@ -61,7 +61,10 @@ def marching_tetrahedras(vertices, tets, sdf, return_tet_idx=False):
     points_d = points_d.to(torch.float32).contiguous()
     sdf_d = sdf_d.to(torch.float32).contiguous()
 
-    verts, faces, tet_idx, _ = _MarchingTets.apply(points_d, sdf_d, tets_d)
+    if torch.is_grad_enabled() and (points_d.requires_grad or sdf_d.requires_grad):
+        verts, faces, tet_idx, _ = _MarchingTets.apply(points_d, sdf_d, tets_d)
+    else:  # nothing to differentiate: skip the autograd bookkeeping (about 15 us of a 0.25 ms call)
+        verts, faces, tet_idx, _ = _C.marching_tetrahedras(points_d, tets_d, sdf_d)
 
     if tets_d.data_ptr() != tets.data_ptr():
         with torch.no_grad():

@@ -16,9 +16,9 @@
 //                   bucket of its id, each of its crossing edges, a 64-bit key (min id << 32 | max id), to
 //                   the key bucket of its min id.  A bucket is a fixed-capacity region; the bucket index is
 //                   the id scaled onto the bucket count, monotone in the id.
-//   k_mtx_sort      one CTA per bucket: the bucket is sorted in shared memory (by counting ranks, which also
-//                   drops duplicates, up to 512 entries; a bitonic network above), written back compacted,
-//                   counted; the counts are also summed per group of 64 buckets.
+//   k_mtx_sort      one CTA per bucket: the bucket is sorted in shared memory by counting ranks inside
+//                   sub-buckets (which also drops duplicates), written back compacted, counted; the counts
+//                   are also summed per group of 64 buckets.
 //   k_mtx_emit      one CTA per bucket: the counts of all buckets before it (whole groups, then its own
 //                   group: one load per thread) number its entries globally, which gives
 //                     key buckets   the global number of each unique key -- bucket order then key order IS
@@ -52,7 +52,10 @@ constexpr int kBucketMean = 128;                // buckets are sized for this ma
 constexpr int kMaxKeyBucketBits = 13;           // at most 8192 key buckets (64 MB of bucket regions)
 constexpr int kMaxSlotBucketBits = 11;          // at most 2048 slot buckets
 constexpr int kSortThreads = 128;
-constexpr int kRankSortMax = 512;               // up to here a bucket is sorted by counting, above by a bitonic network
+#ifndef P3D_MTX_SUBBITS
+#define P3D_MTX_SUBBITS 4
+#endif
+constexpr int kSubBits = P3D_MTX_SUBBITS, kSub = 1 << kSubBits;  // sub-buckets of the counting sort inside a bucket
 constexpr int kGroup = 64;                      // buckets per group of the two-level sum of the bucket counts
 constexpr uint64_t kHole = ~0ull;               // no key and no slot entry has this value
 
@@ -112,12 +115,41 @@ static __device__ __noinline__ void append_valid(int64_t t, uint32_t i0, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// (x, y, z, sdf) per point, 16 bytes: the classify pass gathers four corners per tet, and one 16-byte load per
+// corner costs the L1 a quarter of what three position loads and an sdf load do.  Same values, no arithmetic.
+__global__ void __launch_bounds__(kXThreads) k_mtx_pack(const float *__restrict__ pts, const float *__restrict__ sdf, int64_t P,
+                                                        float4 *__restrict__ packed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) packed[i] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], sdf[i]);
+}
+
 #ifndef P3D_MTX_CTAS
 #define P3D_MTX_CTAS 4
 #endif
+#ifndef P3D_MTX_WIDE
+#define P3D_MTX_WIDE 1
+#endif
+#ifndef P3D_MTX_PACK
+#define P3D_MTX_PACK 1
+#endif
+#ifndef P3D_MTX_GRID
+#define P3D_MTX_GRID 4
+#endif
+// A tet's four int64 indices: one 32-byte load (LDG.256, new with sm_100) when the array is 32-byte aligned, so that
+// every sector fetched is used by the instruction that fetched it; two 16-byte loads otherwise.
+template <bool WIDE>
+__device__ __forceinline__ void tet_load(const longlong2 *p, longlong2 &lo, longlong2 &hi) {
+    if (WIDE) {
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(lo.x), "=l"(lo.y), "=l"(hi.x), "=l"(hi.y) : "l"(p));
+    } else {
+        lo = p[0];
+        hi = p[1];
+    }
+}
+template <bool WIDE>
 __global__ void __launch_bounds__(kXThreads, P3D_MTX_CTAS)
-k_mtx_classify(const float *__restrict__ pts, uint32_t P, int64_t *tets, int64_t T, const float *__restrict__ sdf, XHeader *hdr,
-               XBuckets slots, XBuckets keys, int oriented) {
+k_mtx_classify(const float *__restrict__ pts, uint32_t P, int64_t *tets, int64_t T, const float *__restrict__ sdf,
+               const float4 *__restrict__ packed, XHeader *hdr, XBuckets slots, XBuckets keys, int oriented) {
     const int lane = threadIdx.x & 31;
     longlong2 *t2 = reinterpret_cast<longlong2 *>(tets);
     unsigned long long n1 = 0, n2 = 0, bad = 0;
@@ -127,6 +159,15 @@ k_mtx_classify(const float *__restrict__ pts, uint32_t P, int64_t *tets, int64_t
             ++bad;
             return;
         }
+#if P3D_MTX_PACK
+        // one 16-byte gather per corner from the packed (x, y, z, sdf) copy of the points
+        const float4 c0 = __ldg(packed + id[0]), c1 = __ldg(packed + id[1]), c2 = __ldg(packed + id[2]), c3 = __ldg(packed + id[3]);
+        uint32_t code = (c0.w > 0.f ? 1u : 0u) | (c1.w > 0.f ? 2u : 0u) | (c2.w > 0.f ? 4u : 0u) | (c3.w > 0.f ? 8u : 0u);
+        if (!oriented) {
+            const float ax = c1.x - c0.x, ay = c1.y - c0.y, az = c1.z - c0.z;
+            const float bx = c2.x - c0.x, by = c2.y - c0.y, bz = c2.z - c0.z;
+            const float cx = c3.x - c0.x, cy = c3.y - c0.y, cz = c3.z - c0.z;
+#else
         const float s0 = __ldg(sdf + id[0]), s1 = __ldg(sdf + id[1]), s2 = __ldg(sdf + id[2]), s3 = __ldg(sdf + id[3]);
         uint32_t code = (s0 > 0.f ? 1u : 0u) | (s1 > 0.f ? 2u : 0u) | (s2 > 0.f ? 4u : 0u) | (s3 > 0.f ? 8u : 0u);
         if (!oriented) {
@@ -135,6 +176,7 @@ k_mtx_classify(const float *__restrict__ pts, uint32_t P, int64_t *tets, int64_t
             const float ax = __ldg(q1) - p0x, ay = __ldg(q1 + 1) - p0y, az = __ldg(q1 + 2) - p0z;
             const float bx = __ldg(q2) - p0x, by = __ldg(q2 + 1) - p0y, bz = __ldg(q2 + 2) - p0z;
             const float cx = __ldg(q3) - p0x, cy = __ldg(q3 + 1) - p0y, cz = __ldg(q3 + 2) - p0z;
+#endif
             // a . (b x c) in float32 with the sum of the magnitudes of its terms: about nine roundings, each 2^-24
             // relative, so a result above 2^-20 of that sum (plus a floor against underflow) has the sign of the exact
             // value -- and of the float64 evaluation, whose own error is 2^-29 times smaller
@@ -161,13 +203,17 @@ k_mtx_classify(const float *__restrict__ pts, uint32_t P, int64_t *tets, int64_t
     // two tets per iteration, their index loads issued together: the dependent gathers of one overlap the other's
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    longlong2 lo0, hi0, lo1, hi1;
     for (; t + stride < T; t += 2 * stride) {
-        const longlong2 lo0 = t2[2 * t], hi0 = t2[2 * t + 1];
-        const longlong2 lo1 = t2[2 * (t + stride)], hi1 = t2[2 * (t + stride) + 1];
+        tet_load<WIDE>(t2 + 2 * t, lo0, hi0);
+        tet_load<WIDE>(t2 + 2 * (t + stride), lo1, hi1);
         one(t, lo0, hi0);
         one(t + stride, lo1, hi1);
     }
-    if (t < T) one(t, t2[2 * t], t2[2 * t + 1]);
+    if (t < T) {
+        tet_load<WIDE>(t2 + 2 * t, lo0, hi0);
+        one(t, lo0, hi0);
+    }
     n1 = warp_sum64(n1 | (n2 << 32));  // both below 2^31 per warp
     bad = warp_sum64(bad);
     if (lane == 0) {
@@ -196,36 +242,21 @@ __device__ __forceinline__ unsigned long long cta_excl_scan64(unsigned long long
     return lower + incl - v;
 }
 
-// Sort by counting: entry i goes to slot #{j : key[j] < key[i]}.  Equal keys land on the same slot (they are
-// the same value) and leave holes behind them, which is the de-duplication.  Q entries per thread; s_in is
-// padded with kHole to an even count.
-template <int Q>
-__device__ __forceinline__ void rank_sort(const uint64_t *s_in, uint64_t *s_out, uint32_t n) {
-    uint64_t mine[Q];
-    uint32_t rank[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        const uint32_t i = threadIdx.x + q * kSortThreads;
-        mine[q] = i < n ? s_in[i] : 0ull;
-        rank[q] = 0;
-    }
-    for (uint32_t j = 0; j < n; j += 2) {
-        const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(s_in + j);  // one broadcast load for the warp
-#pragma unroll
-        for (int q = 0; q < Q; ++q) rank[q] += (k.x < mine[q] ? 1u : 0u) + (k.y < mine[q] ? 1u : 0u);
-    }
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-        if (threadIdx.x + q * kSortThreads < n) s_out[rank[q]] = mine[q];
-}
-
 // One CTA per bucket (slot buckets first, then key buckets): sorted and de-duplicated in shared memory, written back
 // to the front of the bucket's region, counted.
+//
+// The sort is by counting: an entry goes to position #{entries smaller than it}; equal keys land on the same position
+// (they are the same value) and leave holes behind them, which is the de-duplication.  To keep the comparisons far
+// below n^2 the bucket is first split into kSub sub-buckets by the next bits of the scaled id (a counting scatter in
+// shared memory); a warp then ranks 32 consecutive entries against the sub-buckets they span only, every comparand
+// one broadcast load for the warp.
 __global__ void __launch_bounds__(kSortThreads)
 k_mtx_sort(XHeader *hdr, XBuckets slots, XBuckets keys) {
-    __shared__ __align__(16) uint64_t s_key[kBucketCap];
-    __shared__ uint64_t s_out[kRankSortMax];
+    __shared__ uint64_t s_tmp[kBucketCap];
+    __shared__ uint64_t s_out[kBucketCap];
+    __shared__ uint32_t s_sub[kSub + 1], s_cur[kSub];
     __shared__ unsigned long long s_warp[kSortThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int job = blockIdx.x;
     const bool is_key = job >= slots.count;
     const XBuckets &cls = is_key ? keys : slots;
@@ -242,44 +273,36 @@ k_mtx_sort(XHeader *hdr, XBuckets slots, XBuckets keys) {
     }
     if (is_key && threadIdx.x == 0) atomicAdd(&hdr->ne, (unsigned long long)filled);
     uint64_t *region = cls.regions + (size_t)b * kBucketCap;
-    uint32_t n2 = 32;
-    while (n2 < n) n2 <<= 1;
-    for (uint32_t i = threadIdx.x; i < n2; i += kSortThreads) s_key[i] = i < n ? region[i] : kHole;
-    uint64_t *sorted = s_key;  // sorted entries with holes where duplicates were
-    if (n <= (uint32_t)kRankSortMax) {
-        for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) s_out[i] = kHole;
-        __syncthreads();
-        if (n <= kSortThreads) rank_sort<1>(s_key, s_out, n);
-        else if (n <= 2 * kSortThreads) rank_sort<2>(s_key, s_out, n);
-        else rank_sort<kRankSortMax / kSortThreads>(s_key, s_out, n);
-        sorted = s_out;
-        __syncthreads();
-    } else {
-        __syncthreads();
-        for (uint32_t k = 2; k <= n2; k <<= 1)
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < n2 / 2; i += kSortThreads) {
-                    const uint32_t l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l + j;
-                    const uint64_t x = s_key[l], y = s_key[r];
-                    if ((x > y) == ((l & k) == 0u)) {
-                        s_key[l] = y;
-                        s_key[r] = x;
-                    }
-                }
-                __syncthreads();
-            }
-        bool dup[kBucketCap / kSortThreads];
-#pragma unroll
-        for (int q = 0; q < kBucketCap / kSortThreads; ++q) {
-            const uint32_t i = threadIdx.x + q * kSortThreads;
-            dup[q] = i > 0 && i < n && s_key[i] == s_key[i - 1];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kBucketCap / kSortThreads; ++q)
-            if (dup[q]) s_key[threadIdx.x + q * kSortThreads] = kHole;
-        __syncthreads();
+    const uint64_t scale = cls.scale;
+    const int id_shift = is_key ? 32 : 4;  // key: min id << 32 | max id; slot entry: tet << 4 | code
+    auto sub_of = [&](uint64_t e) { return (uint32_t)(((e >> id_shift) * scale) >> (32 - kSubBits)) & (uint32_t)(kSub - 1); };
+    if (threadIdx.x <= kSub) s_sub[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) atomicAdd(&s_sub[sub_of(region[i]) + 1], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k <= kSub; ++k) s_sub[k] += s_sub[k - 1];  // s_sub[k] = first position of sub-bucket k
     }
+    __syncthreads();
+    if (threadIdx.x < kSub) s_cur[threadIdx.x] = s_sub[threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) {
+        const uint64_t e = region[i];
+        s_tmp[atomicAdd(&s_cur[sub_of(e)], 1u)] = e;
+        s_out[i] = kHole;
+    }
+    __syncthreads();
+    for (uint32_t base = warp * 32; base < n; base += kSortThreads) {
+        const uint32_t i = base + lane;
+        const uint64_t e = s_tmp[i < n ? i : n - 1];
+        const uint32_t sub = sub_of(e);
+        const uint32_t from = s_sub[__shfl_sync(kFull, sub, 0)], to = s_sub[__shfl_sync(kFull, sub, 31) + 1];
+        uint32_t rank = 0;
+        for (uint32_t j = from; j < to; ++j) rank += s_tmp[j] < e ? 1u : 0u;
+        if (i < n) s_out[from + rank] = e;
+    }
+    __syncthreads();
+    const uint64_t *sorted = s_out;  // sorted entries with holes where duplicates were
     // a contiguous run of sorted entries per thread; the survivors go back to the front of the region, in order
     const uint32_t per = (n + kSortThreads - 1) / kSortThreads;
     const uint32_t i0 = threadIdx.x * per;
@@ -424,7 +447,7 @@ k_mtx_faces(const int64_t *__restrict__ tets, const XHeader *__restrict__ hdr, c
 }
 
 struct XLayout {
-    size_t header, cursors_slots, cursors_keys, groups_slots, groups_keys, zeroed, counts_slots, counts_keys, ubase, list1, list2, regions_slots, regions_keys, total;
+    size_t header, cursors_slots, cursors_keys, groups_slots, groups_keys, zeroed, counts_slots, counts_keys, packed, ubase, list1, list2, regions_slots, regions_keys, total;
     int slot_buckets, key_buckets;
     uint64_t slot_scale, key_scale;
 };
@@ -452,6 +475,7 @@ bool x_layout(int64_t T, int64_t P, int64_t slot_cap, int64_t key_cap, XLayout *
     l->counts_slots = off;  off += up256((size_t)l->slot_buckets * 8);
     l->counts_keys = off;   off += up256((size_t)l->key_buckets * 8);
     l->ubase = off;         off += up256((size_t)(l->key_buckets + 1) * 4);
+    l->packed = off;        off += up256(P3D_MTX_PACK ? (size_t)P * 16 : 0);
     l->list1 = off;         off += up256((size_t)slot_cap * 8);
     l->list2 = off;         off += up256((size_t)slot_cap * 8);
     l->regions_slots = off; off += (size_t)l->slot_buckets * kBucketCap * 8;
@@ -533,9 +557,14 @@ p3d_status p3d_mt_extract(const float *points, int64_t num_points, int64_t *tets
     const int sms = sm_count();
     {
         const int64_t want = (num_tets + 2 * kXThreads - 1) / (2 * kXThreads);
-        const int64_t cap = (int64_t)sms * 16;
-        k_mtx_classify<<<(unsigned)(want < cap ? want : cap), kXThreads, 0, s>>>(points, (uint32_t)num_points, tets, num_tets, sdf, hdr,
-                                                                              slots, keys, oriented);
+        const int64_t cap = (int64_t)sms * P3D_MTX_GRID;
+        float4 *packed = reinterpret_cast<float4 *>(base + l.packed);
+        if (P3D_MTX_PACK) k_mtx_pack<<<(unsigned)((num_points + kXThreads - 1) / kXThreads), kXThreads, 0, s>>>(points, sdf, num_points, packed);
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        if ((reinterpret_cast<uintptr_t>(tets) & 31) == 0 && P3D_MTX_WIDE)
+            k_mtx_classify<true><<<grid, kXThreads, 0, s>>>(points, (uint32_t)num_points, tets, num_tets, sdf, packed, hdr, slots, keys, oriented);
+        else
+            k_mtx_classify<false><<<grid, kXThreads, 0, s>>>(points, (uint32_t)num_points, tets, num_tets, sdf, packed, hdr, slots, keys, oriented);
     }
     const int jobs = l.slot_buckets + l.key_buckets;
     k_mtx_sort<<<jobs, kSortThreads, 0, s>>>(hdr, slots, keys);
