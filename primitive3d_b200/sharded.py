@@ -167,6 +167,133 @@ def marching_cubes_slab(slab, thresh, x_begin, global_rx, lower=None, upper=None
 
 
 # ---------------------------------------------------------------------------------------------
+# A shard that lives in HOST memory: uploaded part by part while the parts already on the device are extracted.
+# ---------------------------------------------------------------------------------------------
+_part_counts = {}   # (slab shape, parts) -> [V_k] of the last extraction (sizes the parts' speculative vertex segments)
+
+
+def _part_bounds(owned, parts):
+    """Plane ranges [a, b) of the parts of a shard: equal, multiples of 8 planes (the tile depth) but the last."""
+    step = max(8, -(-owned // max(1, parts)) + 7 & ~7)
+    edges = list(range(0, owned, step)) + [owned]
+    if len(edges) > 2 and edges[-1] - edges[-2] < 8:
+        del edges[-2]          # a sliver at the end joins the part before it (a part needs two planes at least)
+    return list(zip(edges[:-1], edges[1:]))
+
+
+def marching_cubes_slab_host(host_slab, thresh, x_begin, global_rx, lower=None, upper=None, group=None, parts=None,
+                             out_vertices=None, out_faces=None, device=None, distributed=True):
+    """marching_cubes_slab for a shard in HOST memory (pinned for full PCIe speed), upload overlapped with extraction.
+
+    The shard is cut into `parts` plane ranges that behave as consecutive shards of a world of `world * parts`:
+    while part k + 1 uploads (a second stream, two device buffers), part k runs its tile pass and exports its exchange
+    payload; ONE all-gather then carries every part's payload, and the face passes of all parts run against it (they
+    read the workspaces only, the grid data has left the device by then).  The host waits once, for the gathered
+    counts.  Numbering: part by part within the rank, rank by rank (concatenated in rank order the shards are the
+    single-GPU mesh of the whole grid over a vertex array numbered part by part).
+
+    out_vertices / out_faces: optional pinned CPU tensors ([>= V_r, 3] float32, [>= F_r, 3] int32) that receive the
+    shard; the returned SlabMesh then holds views of them (complete on return).  Otherwise device tensors.
+    distributed=False: the slab is the whole grid whatever process group exists (prim3d.marching_cubes on a CPU tensor)."""
+    world = dist.get_world_size(group) if distributed and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if distributed and dist.is_initialized() else 0
+    if host_slab.is_cuda or not host_slab.is_contiguous() or host_slab.dim() != 3 or host_slab.dtype not in capi.GRID_DTYPES:
+        raise ValueError("host_slab must be a contiguous CPU tensor [planes, Ry, Rz] of a supported dtype")
+    x0, x1 = slab_range(global_rx, world, rank)
+    if x0 != x_begin or host_slab.shape[0] != min(x1 + 1, global_rx) - x0:
+        raise ValueError(f"rank {rank}: slab must hold planes [{x0}, {min(x1 + 1, global_rx)})")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    owned, planes = x1 - x0, host_slab.shape[0]
+    ry, rz = int(host_slab.shape[1]), int(host_slab.shape[2])
+    lower = [0.0, 0.0, 0.0] if lower is None else lower
+    upper = [float(global_rx), float(ry), float(rz)] if upper is None else upper
+    if parts is None:
+        parts = max(1, min(16, owned // 32))
+    bounds = _part_bounds(owned, parts)
+    parts = len(bounds)
+    L, dtype = capi.lib(), capi.GRID_DTYPES[host_slab.dtype]
+    descs, sizes = [], []
+    for a, b in bounds:
+        held = min(b + 1, planes) - a                      # the part's planes plus the halo plane, if there is one
+        d = capi.McDesc.make((held, ry, rz), thresh, lower, upper, owned_x=b - a, x_origin=x0 + a, global_rx=global_rx)
+        descs.append(d)
+        sizes.append(capi._desc_sizes(d))
+    key = (tuple(int(v) for v in host_slab.shape), parts)
+    for attempt in range(2):
+        prev = _part_counts.get(key)
+        caps = [min(v + v // 16 + 4096, 2 ** 31 - 1) for v in prev] if prev else [sz[1] for sz in sizes]
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream()
+            up = torch.cuda.Stream()
+            depth = max(min(b + 1, planes) - a for a, b in bounds)
+            bufs = [torch.empty((depth, ry, rz), dtype=host_slab.dtype, device=dev) for _ in range(min(2, parts))]
+            wss = [torch.empty(sz[0], dtype=torch.uint8, device=dev) for sz in sizes]
+            seg = [0]
+            for c in caps:
+                seg.append(seg[-1] + int(c))
+            vbuf = torch.empty((seg[-1], 3), dtype=torch.float32, device=dev)
+            words = L.p3d_mc_exchange_words(ctypes.byref(descs[0]))
+            payload = torch.empty(parts * words, dtype=torch.int32, device=dev)
+            stream = ctypes.c_void_p(cur.cuda_stream)
+            up.wait_stream(cur)
+            released = [None] * len(bufs)
+            for k, (a, b) in enumerate(bounds):
+                held = min(b + 1, planes) - a
+                buf = bufs[k % len(bufs)][:held]
+                with torch.cuda.stream(up):
+                    if released[k % len(bufs)] is not None:
+                        up.wait_event(released[k % len(bufs)])   # the tile pass that read this buffer is over
+                    buf.copy_(host_slab[a:a + held], non_blocking=True)
+                    arrived = torch.cuda.Event()
+                    arrived.record(up)
+                cur.wait_event(arrived)
+                capi.check(L.p3d_mc_tile_async(ctypes.byref(descs[k]), buf.data_ptr(), dtype, wss[k].data_ptr(), wss[k].numel(),
+                                               vbuf[seg[k]:].data_ptr() if caps[k] else None, int(caps[k]), stream))
+                capi.check(L.p3d_mc_export_exchange(ctypes.byref(descs[k]), wss[k].data_ptr(),
+                                                    payload[k * words:].data_ptr(), stream))
+                released[k % len(bufs)] = torch.cuda.Event()
+                released[k % len(bufs)].record(cur)
+            if world > 1:
+                gathered = torch.empty(world * parts * words, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(gathered, payload, group=group)
+            else:
+                gathered = payload
+            counts = unpack_counts(gathered, world * parts, words)      # the only synchronisation
+            mine = counts[rank * parts:(rank + 1) * parts]
+            if len(_part_counts) > 64:
+                _part_counts.clear()
+            _part_counts[key] = [int(c[0]) for c in mine]
+            if any(int(c[0]) > cap for c, cap in zip(mine, caps)):
+                if attempt == 0:
+                    continue      # a segment was too small (first call on a busy field): once more with the counts known
+                raise capi.P3DError(capi.P3D_ERR_INVALID, "marching_cubes_slab_host: counts changed between two passes")
+            v_off, f_off, v_tot, f_tot = exclusive_offsets(counts, rank * parts)
+            if v_tot > 2 ** 31 - 1:
+                raise OverflowError("global vertex count exceeds the int32 face-index contract")
+            V_r, F_r = sum(int(c[0]) for c in mine), sum(int(c[1]) for c in mine)
+            fbuf = torch.empty((F_r, 3), dtype=torch.int32, device=dev)
+            f_at = 0
+            for k in range(parts):
+                F_k = int(mine[k][1])
+                capi.check(L.p3d_mc_faces_exchanged(ctypes.byref(descs[k]), wss[k].data_ptr(), gathered.data_ptr(), rank * parts + k,
+                                                    world * parts, fbuf[f_at:].data_ptr() if F_k else None, F_k, stream))
+                f_at += F_k
+            pieces = [vbuf[seg[k]:seg[k] + int(mine[k][0])] for k in range(parts)]
+            if out_vertices is not None or out_faces is not None:
+                if out_vertices is None or out_faces is None or out_vertices.shape[0] < V_r or out_faces.shape[0] < F_r:
+                    raise ValueError("out_vertices / out_faces must both be given and hold the shard")
+                at = 0
+                for piece in pieces:
+                    out_vertices[at:at + piece.shape[0]].copy_(piece, non_blocking=True)
+                    at += piece.shape[0]
+                out_faces[:F_r].copy_(fbuf, non_blocking=True)
+                cur.synchronize()
+                return SlabMesh(out_vertices[:V_r], out_faces[:F_r], v_off, f_off, v_tot, f_tot)
+            verts = torch.cat(pieces) if parts > 1 else pieces[0]
+            return SlabMesh(verts, fbuf, v_off, f_off, v_tot, f_tot)
+
+
+# ---------------------------------------------------------------------------------------------
 # The same extraction through the single C entry p3d_mc_sharded_extract, over a raw NCCL communicator
 # (what a C / C++ host would do; torch.distributed only carries the unique id to the other ranks).
 # ---------------------------------------------------------------------------------------------

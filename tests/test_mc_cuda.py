@@ -242,6 +242,32 @@ def test_host_streamed_extraction_equals_single_shot(shape, planes, dtype):
     assert torch.equal(v2, v) and torch.equal(f2, f)
 
 
+@pytest.mark.parametrize("shape,parts,dtype", [((72, 24, 140), 4, np.float32), ((37, 20, 64), 3, np.float32),
+                                                ((16, 16, 16), 1, np.float32), ((50, 12, 33), 6, np.float64),
+                                                ((130, 9, 40), 16, np.float16)])
+def test_host_shard_uploaded_in_overlapped_parts(shape, parts, dtype):
+    """sharded.marching_cubes_slab_host on one GPU (the shard is the whole grid): the parts behave as consecutive
+    shards, faces in voxel-major order over a vertex array numbered part by part; device or pinned-host outputs; a
+    noise field overflows the first call's speculative vertex segments and is redone with the counts known."""
+    from primitive3d_b200 import capi, sharded
+    g = inputs.noise(shape, sum(shape)).astype(dtype)
+    host = torch.from_numpy(np.ascontiguousarray(g)).pin_memory()
+    lower, upper = [-1.0, 0.5, 2.0], [3.0, 4.5, 2.5]
+    v0, f0 = capi.marching_cubes(host.cuda(), 0.05, lower, upper)
+    sharded._part_counts.clear()
+    for _ in range(2):      # without, then with remembered counts
+        m = sharded.marching_cubes_slab_host(host, 0.05, 0, shape[0], lower, upper, parts=parts, distributed=False)
+        torch.cuda.synchronize()
+        assert m.vertices.is_cuda and (m.v_offset, m.f_offset) == (0, 0)
+        assert (m.num_vertices_total, m.num_faces_total) == (v0.shape[0], f0.shape[0])
+        assert_same_mesh(m.vertices.cpu().numpy(), m.faces.cpu().numpy(), v0.cpu().numpy(), f0.cpu().numpy(), ordered_faces=True)
+    hv = torch.empty((v0.shape[0] + 3, 3)).pin_memory()
+    hf = torch.empty((f0.shape[0], 3), dtype=torch.int32).pin_memory()
+    m2 = sharded.marching_cubes_slab_host(host, 0.05, 0, shape[0], lower, upper, parts=parts, out_vertices=hv, out_faces=hf,
+                                          distributed=False)
+    assert not m2.vertices.is_cuda and torch.equal(m2.vertices, m.vertices.cpu()) and torch.equal(m2.faces, m.faces.cpu())
+
+
 def test_batched_small_grids_equal_one_by_one():
     """p3d_mc_extract_batch: many small grids queued back to back, one host wait; every mesh equals the one the
     single call gives (including a grid dense enough to overflow its speculative buffers, and an empty one)."""

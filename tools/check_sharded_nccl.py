@@ -39,6 +39,13 @@ def main():
     # numbering-independent checksums of the sharded mesh (primitive3d_b200/verify.py), taken shard-wise
     from primitive3d_b200 import verify
     sums = verify.mesh_checksums(out.vertices, out.faces, out.v_offset, out.f_offset, float(x0))
+    # the shard from HOST memory, uploaded in parts overlapped with their tile passes: the same mesh, numbered part by part
+    host = slab.cpu().pin_memory()
+    hosted = sharded.marching_cubes_slab_host(host, 0.0, x0, n, parts=4)
+    assert (hosted.v_offset, hosted.f_offset, hosted.num_vertices_total, hosted.num_faces_total) == \
+        (out.v_offset, out.f_offset, out.num_vertices_total, out.num_faces_total)
+    assert verify.mesh_checksums(hosted.vertices, hosted.faces, hosted.v_offset, hosted.f_offset, float(x0)) == sums, \
+        "checksums of the host-pipelined shards differ"
     shards = [None] * world
     dist.all_gather_object(shards, (out.vertices.cpu(), out.faces.cpu(), out.v_offset, out.f_offset))
     if rank == 0:
@@ -52,7 +59,7 @@ def main():
         assert torch.equal(fs, f.cpu()), "faces differ"
         assert verify.mesh_checksums(v, f, single=True) == sums, "checksums of the sharded and the single-GPU mesh differ"
         print(f"sharded NCCL check OK: world={world} n={n} V={v.shape[0]} F={f.shape[0]} "
-              f"(python driver == p3d_mc_sharded_extract == single GPU; checksums {sums[0]:016x} {sums[1]:016x})")
+              f"(python driver == p3d_mc_sharded_extract == host-pipelined shards == single GPU; checksums {sums[0]:016x} {sums[1]:016x})")
     dist.barrier()
     dist.destroy_process_group()
 
