@@ -99,7 +99,7 @@ def per_line(rep, launch, func, top):
     print(f"warp instructions {tot}, samples {smp}")
     print("stall samples: " + ", ".join(f"{s[6:]}={100 * v / smp:.1f}%" for (s, _), v in sorted(zip(st, stall_tot), key=lambda t: -t[1]) if v * 100 > smp))
     src = {}
-    for f in ("mc_kernels.cu", "mt_kernels.cu", "scan_utils.cuh"):
+    for f in sorted(os.listdir(os.path.join(ROOT, "primitive3d_b200", "csrc"))):
         p = os.path.join(ROOT, "primitive3d_b200", "csrc", f)
         if os.path.exists(p):
             src[f] = {i + 1: s.rstrip() for i, s in enumerate(open(p))}

@@ -1,5 +1,6 @@
 """Times prim3d.marching_tetrahedras on the Kuhn grid (BASELINE configs[3] at n = 128).
   python tools/prof_mt.py [n] [calls]      calls = 0: ONE call, for an ncu capture"""
+import os
 import sys
 import time
 
@@ -32,6 +33,8 @@ if calls == 0:   # two calls: the second one runs with capacities remembered fro
     torch.cuda.synchronize()
     print(v.shape, f.shape)
     sys.exit(0)
+if os.environ.get("MT_PREORIENTED"):   # every call sees tets that are oriented already: no flips, no write traffic
+    prim3d.marching_tetrahedras(P, T, S)
 clones = [T.clone() for _ in range(calls + 3)]
 for i in range(3):
     v, f = prim3d.marching_tetrahedras(P, clones[i], S)
