@@ -226,8 +226,16 @@ def main():
             v, f = prim3d._C.marching_cubes(slab, 0.0, box_lo, box_hi)
             return sharded.SlabMesh(v, f, 0, 0, v.shape[0], f.shape[0])
     else:
-        def step():
-            return sharded.marching_cubes_slab(slab, 0.0, x0, n)
+        # several GPUs: ONE C call per step, p3d_mc_sharded_extract over a raw NCCL communicator (tile pass, exchange
+        # payload, ncclAllGather, face pass, one host wait); P3D_BENCH_DRIVER=python times the torch.distributed driver
+        if os.environ.get("P3D_BENCH_DRIVER", "c") == "python":
+            def step():
+                return sharded.marching_cubes_slab(slab, 0.0, x0, n)
+        else:
+            comm = sharded.nccl_comm_init()
+
+            def step():
+                return sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world)
 
     for _ in range(args.warmup):
         out = step()

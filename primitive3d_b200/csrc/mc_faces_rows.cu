@@ -13,12 +13,18 @@
 // split into what a row owns by itself (x-edge and z-edge masks of (x,y) and z-edge mask of (x+1,y), with the id
 // of the first crossing of each word: table entry + popcounts along the piece) and what a row shares with the row
 // after it (the two y-edge masks).  The row-own part of row y + 1 IS q5 q6 q7 of row y, so every mask and every
-// rank is computed once per row and carried in registers to the next iteration: per row a lane loads two bit
-// words and two table entries, where the chunk form of this pass (k_faces) loads four rows and recomputes all
-// eight masks for every cell row.  The sparse work is the same as there: the words with active cells park
-// {corner words, masks, first ids} in shared memory, then one active cell per lane (case -> packed triangle row)
-// and one triangle per lane (three  first id + popc(mask below z)  ranks, 12-byte store), in voxel-major cell
-// order and table order inside a cell (:194-208).
+// rank is computed once per row: a row writes its own {mask, first id} pairs to the lane's slot of a shared-memory
+// rank table once, as quad (t & 1) of the slot (t = the row's number in the task), and is read from there as the
+// upper row of one pair and, untouched, as the lower row of the next (the case table is staged twice, the copy for
+// odd rows with the two quads swapped).  Per row a lane loads two bit words and two table entries, where the chunk
+// form of this pass (k_faces) loads four rows and recomputes all eight masks for every cell row.
+//
+// Triangles are placed without a cell list and without ballots: the tile pass left the triangle count of every
+// 32-cell word (a byte per word, four to a piece), so an exclusive scan over the lanes gives each lane the position
+// of its word's triangles in the row.  The lane then walks its active cells, last to first (case -> packed
+// triangle row), and drops one entry per triangle -- (slot, bit, three pair indices) -- into a list in shared
+// memory at that position; the list is consumed one triangle per lane: three  first id + popc(mask below z)
+// ranks from the rank table, 12-byte store, voxel-major cell order and table order inside a cell (:194-208).
 //
 // Face offsets: the first face of a task is the sum of the rounds before its round, of the chunks before its
 // chunk in the round and of the pieces before its first piece in the chunk (final data written by the tile

@@ -6,9 +6,9 @@
 // /root/reference/src/prim3d/Utility/marching_cubes.cu.
 //
 // One persistent kernel, every CTA resident, three phases separated by a device-wide barrier:
-//   1  a warp per 32 bit words (32 samples each) of the batch: inside bits of the four rows a word's cells touch
-//      (value > thresh, :25), by coalesced loads and ballots; crossing masks, vertex counts (:29-45) and triangle
-//      counts (:48-66) per word; CTA totals
+//   1  a thread per bit word (32 samples of a row) of the batch: inside bits of the four rows a word's cells touch
+//      (value > thresh, :25), read in rounds of 32 independent predicated loads; crossing masks, vertex counts
+//      (:29-45) and triangle counts (:48-66) per word, packed into one 32-bit count word; CTA totals
 //   2  exclusive prefix over the words (CTA totals -> per-word first vertex id / first face index, numbering restarts
 //      at every grid); vertices of the word's own +x / +y / +z edges, interpolated in the reference's fp32 order
 //      (:105-109, :298)
@@ -32,6 +32,7 @@ __constant__ uint64_t c_case_table_small[256] = P3D_MC_CASE_TABLE_INIT;
 constexpr int kSmallThreads = 256;
 constexpr int kSmallSlab = kSmallThreads;  // words a CTA scans at a time
 
+// Ownership of the cube edges, from which phase 3 builds its per-edge {mask, first id} tables:
 // cube edge e (numbering of :178-192) -> which of the cell's four rows owns it (0 a = (x,y), 1 b = (x+1,y),
 // 2 c = (x+1,y+1), 3 d = (x,y+1)), its axis (0 x, 1 y, 2 z) and whether it sits at sample z + 1
 //   e:    0  1  2  3  4  5  6  7  8  9 10 11

@@ -351,8 +351,14 @@ def marching_cubes_slab_c(slab, thresh, x_begin, global_rx, comm, rank, world, v
     L = capi.lib()
     dev = slab.device
     ws_bytes, hint = capi._desc_sizes(desc)
+    key = tuple(int(s) for s in slab.shape)
+    if vertex_capacity is None:
+        vertex_capacity = capacity_for(slab.shape)
     vertex_capacity = hint if vertex_capacity is None else int(vertex_capacity)
-    face_capacity = 2 * vertex_capacity if face_capacity is None else int(face_capacity)
+    if face_capacity is None:
+        f_prev = _last_face_count.get(key)
+        face_capacity = 2 * vertex_capacity if f_prev is None else f_prev + f_prev // 16 + 4096
+    face_capacity = int(face_capacity)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     vbuf = torch.empty((vertex_capacity, 3), dtype=torch.float32, device=dev)
     fbuf = torch.empty((face_capacity, 3), dtype=torch.int32, device=dev)
@@ -367,6 +373,10 @@ def marching_cubes_slab_c(slab, thresh, x_begin, global_rx, comm, rank, world, v
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     pairs = [(counts[2 * r], counts[2 * r + 1]) for r in range(world)]
     V, F = pairs[rank]
+    if len(_last_vertex_count) > 64:
+        _last_vertex_count.clear()
+        _last_face_count.clear()
+    _last_vertex_count[key], _last_face_count[key] = V, F
     v_off, f_off, v_tot, f_tot = exclusive_offsets(pairs, rank)
     verts = capi.mc_vertices(desc, slab, ws, V, vbuf)
     faces = fbuf[:F] if F <= face_capacity else capi.mc_faces(desc, ws, F, v_off)
