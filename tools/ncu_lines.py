@@ -20,19 +20,24 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def sass_lines(func, lib):
+def sass_lines(func, lib, nrows=None):
+    """((file, line), SASS text) per instruction of the function whose section name contains `func`.  A template has
+    one section per instance: the one with exactly `nrows` instructions (the launch that was profiled) is taken."""
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, capture_output=True)
+    sections = []
     for f in sorted(os.listdir(d)):
         if not f.endswith(".cubin"):
             continue
         text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, f)], capture_output=True, text=True).stdout
         if func not in text:
             continue
-        out, cur, on = [], None, False
+        cur, on = None, False
         for ln in text.splitlines():
             if re.match(r"\s*\.section\s+\.text\.", ln) or ln.startswith(".text."):
                 on = func in ln
+                if on:
+                    sections.append([])
                 continue
             if not on:
                 continue
@@ -40,10 +45,10 @@ def sass_lines(func, lib):
             if m:
                 cur = (m.group(1).split("/")[-1], int(m.group(2)))
             elif re.match(r"\s+/\*[0-9a-f]{4,5}\*/", ln):
-                out.append((cur, ln.strip()))
-        if out:
-            return out
-    return []
+                sections[-1].append((cur, ln.strip()))
+    sections = [sec for sec in sections if sec]
+    exact = [sec for sec in sections if nrows is not None and len(sec) == nrows]
+    return exact[0] if exact else (sections[0] if sections else [])
 
 
 def main():
@@ -63,7 +68,7 @@ def main():
     hdr = rows[h]
     ii, ti, si = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
     body = [r for r in rows[h + 1:] if len(r) > ti and r[0] != "Kernel Name"]
-    lines = sass_lines(args.func, args.lib)
+    lines = sass_lines(args.func, args.lib, len(body))
     print(f"# {len(body)} SASS rows in the report, {len(lines)} in the local cubin")
     src = {}
     for f in os.listdir(os.path.join(ROOT, "primitive3d_b200", "csrc")):

@@ -43,20 +43,25 @@ def launch_table(rep):
     print("units: " + ", ".join(f"{k}={units[i]}" for k, i in idx))
 
 
-def sass_lines(func):
+def sass_lines(func, nrows=None):
+    """(file, line) per SASS instruction of the function whose section name contains `func`.  A template has one
+    section per instance: the one with exactly `nrows` instructions (the launch that was profiled) is taken."""
     so = os.path.join(ROOT, "primitive3d_b200", "libprim3d_b200.so")
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=d, capture_output=True)
-    out, cur, on = [], None, False
+    sections = []
     for f in sorted(os.listdir(d)):
         if not f.endswith(".cubin"):
             continue
         text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, f)], capture_output=True, text=True).stdout
         if func not in text:
             continue
+        cur, on = None, False
         for ln in text.splitlines():
             if re.match(r"\s*\.section\s+\.text\.", ln) or ln.startswith(".text."):
                 on = func in ln
+                if on:
+                    sections.append([])
                 continue
             if not on:
                 continue
@@ -64,10 +69,10 @@ def sass_lines(func):
             if m:
                 cur = (m.group(1).split("/")[-1], int(m.group(2)))
             elif re.match(r"\s+/\*[0-9a-f]{4,5}\*/", ln):
-                out.append(cur)
-        if out:
-            break
-    return out
+                sections[-1].append(cur)
+    sections = [sec for sec in sections if sec]
+    exact = [sec for sec in sections if nrows is not None and len(sec) == nrows]
+    return exact[0] if exact else (sections[0] if sections else [])
 
 
 def per_line(rep, launch, func, top):
@@ -83,7 +88,7 @@ def per_line(rep, launch, func, top):
             break
         if len(r) > ii:
             body.append(r)
-    lines = sass_lines(func)
+    lines = sass_lines(func, len(body))
     print(f"{rows[0][1][:70]}: {len(body)} SASS rows, {len(lines)} in the local cubin")
     agg, stall_tot = {}, [0] * len(st)
     for r, ln in zip(body, lines):
