@@ -172,6 +172,23 @@ p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, con
                                 const int64_t *vertex_capacities, int32_t *const *faces,
                                 const int64_t *face_capacities, int64_t *counts_host, void *stream);
 
+/* Block-sparse form: p3d_mc_extract over a dense grid of which only the listed TILES are examined (a level set
+ * touches a few per cent of a large grid; the caller usually knows where, e.g. from the previous frame or from a
+ * coarse pass).  A tile is 8 x 8 rows x 128 samples: tile id = (x / 8 * ceil(ry / 8) + y / 8) * ceil(rz / 128) + z / 128.
+ *   grid       float32 (dtype = P3D_F32);
+ *   tiles      device array of num_tiles DISTINCT tile ids; it must hold every tile that contains a sample whose +x,
+ *              +y or +z edge is crossed, or a cell with mixed corners (then the mesh is the dense call's mesh);
+ *              sorted ids keep neighbouring tiles close in time (L2 reuse of the shared halo planes);
+ *   workspace  p3d_mc_workspace_bytes(desc), zeroed by the call;
+ *   outputs as in p3d_mc_extract (complete iff V <= vertex_capacity and F <= face_capacity; otherwise call again
+ *   with buffers of the returned sizes).  Vertices are numbered tile by tile in LIST order, faces are in voxel-major
+ *   order.  The tile pass reads 32 KB of samples per listed tile instead of the whole grid; the face pass still walks
+ *   every row (one count word per 128 samples).  Whole grids only (no halo plane).  The reference has no such entry. */
+p3d_status p3d_mc_extract_sparse(const p3d_mc_desc *desc, const void *grid, int dtype, const uint32_t *tiles,
+                                 int64_t num_tiles, void *workspace, size_t workspace_bytes, float *vertices,
+                                 int64_t vertex_capacity, int32_t *faces, int64_t face_capacity,
+                                 int64_t *counts_host, void *stream);
+
 /* Profiling hook (bench.py times each kernel with CUDA events through it): runs ONE stage of
  * p3d_mc_count asynchronously on `stream` -- 0: reset scan state, 1: tile pass (classify,
  * count, look-back, vertices).  The face stage (scan over chunks + faces) is p3d_mc_faces itself. */

@@ -77,6 +77,8 @@ def lib():
         L.p3d_mc_sharded_extract.restype = ctypes.c_int
         L.p3d_mc_sharded_extract.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, i64, vp, i64,
                                              ctypes.POINTER(i64), vp]
+        L.p3d_mc_extract_sparse.restype = ctypes.c_int
+        L.p3d_mc_extract_sparse.argtypes = [dp, vp, ctypes.c_int, vp, i64, vp, sz, vp, i64, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_extract_host.restype = ctypes.c_int
         L.p3d_mc_extract_host.argtypes = [dp, vp, ctypes.c_int, i64, vp, i64, vp, i64, ctypes.POINTER(i64), vp, sz]
         L.p3d_mc_extract_host_arena_bytes.restype = sz
@@ -352,6 +354,59 @@ def marching_cubes(grid, thresh, lower=None, upper=None, vertex_capacity=None):
     desc = McDesc.make(grid.shape, thresh, lower, upper)
     V, F, ws, vbuf = mc_count(desc, grid, vertex_capacity=vertex_capacity)
     return mc_vertices(desc, grid, ws, V, vbuf), mc_faces(desc, ws, F)
+
+
+def active_tiles(grid, thresh):
+    """The tile list p3d_mc_extract_sparse needs for the CUDA tensor `grid`, as a sorted int32 tensor: every tile
+    (8 x 8 rows x 128 samples, id = (x // 8 * ceil(ry / 8) + y // 8) * ceil(rz / 128) + z // 128) that holds a sample
+    whose +x / +y / +z edge is crossed or a cell with mixed corners.  Plain torch ops over the whole grid: a helper for
+    tests and for callers without a cheaper source of the list (the point of the sparse form is NOT to look at the
+    whole grid; a coarse pass or the previous frame usually says where the surface is)."""
+    inside = grid.to(torch.float32) > thresh
+    rx, ry, rz = inside.shape
+    ex, ey, ez = inside[:-1] ^ inside[1:], inside[:, :-1] ^ inside[:, 1:], inside[:, :, :-1] ^ inside[:, :, 1:]
+    need = torch.zeros_like(inside)
+    need[:-1] |= ex
+    need[:, :-1] |= ey
+    need[:, :, :-1] |= ez
+    if min(rx, ry, rz) > 1:
+        cell = ex[:, :-1, :-1] | ex[:, 1:, :-1] | ex[:, :-1, 1:] | ex[:, 1:, 1:]
+        cell |= ey[:-1, :, :-1] | ey[1:, :, :-1] | ey[:-1, :, 1:] | ey[1:, :, 1:]
+        cell |= ez[:-1, :-1, :] | ez[1:, :-1, :] | ez[:-1, 1:, :] | ez[1:, 1:, :]
+        need[:-1, :-1, :-1] |= cell
+    nxb, nyb, npz = -(-rx // 8), -(-ry // 8), -(-rz // 128)
+    padded = torch.zeros((nxb * 8, nyb * 8, npz * 128), dtype=torch.bool, device=grid.device)
+    padded[:rx, :ry, :rz] = need
+    tiles = padded.view(nxb, 8, nyb, 8, npz, 128).any(dim=5).any(dim=3).any(dim=1)
+    return tiles.reshape(-1).nonzero().reshape(-1).to(torch.int32)
+
+
+def marching_cubes_sparse(grid, thresh, tiles, lower=None, upper=None, vertex_capacity=None, face_capacity=None):
+    """p3d_mc_extract_sparse: marching cubes of the listed tiles of a dense CUDA grid (see include/prim3d_b200.h);
+    tiles = int32 CUDA tensor of distinct tile ids, e.g. active_tiles(grid, thresh) -> (vertices, faces)."""
+    dtype = _grid_ok(grid)
+    if grid.dtype != torch.float32:
+        raise ValueError("the block-sparse form takes float32 grids")
+    if not (tiles.is_cuda and tiles.dtype == torch.int32 and tiles.is_contiguous() and tiles.dim() == 1):
+        raise ValueError("tiles must be a contiguous int32 CUDA vector")
+    desc = McDesc.make(grid.shape, thresh, lower, upper)
+    ws_bytes, hint = _desc_sizes(desc)
+    n = int(tiles.numel())
+    vcap = min(hint, n * 24576 + 1) if vertex_capacity is None else int(vertex_capacity)   # a tile has at most 24576 vertices
+    fcap = 2 * vcap if face_capacity is None else int(face_capacity)
+    with _on_device(grid.device):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grid.device)
+        for _ in range(2):
+            verts = torch.empty((vcap, 3), dtype=torch.float32, device=grid.device)
+            faces = torch.empty((fcap, 3), dtype=torch.int32, device=grid.device)
+            counts = (ctypes.c_int64 * 2)()
+            check(lib().p3d_mc_extract_sparse(ctypes.byref(desc), grid.data_ptr(), dtype, tiles.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                              verts.data_ptr(), vcap, faces.data_ptr(), fcap, counts, _stream()))
+            V, F = counts[0], counts[1]
+            if V <= vcap and F <= fcap:
+                return verts[:V], faces[:F]
+            vcap, fcap = max(V, 1), max(F, 1)
+    raise P3DError(P3D_ERR_INVALID, "marching_cubes_sparse: counts changed between two passes over the same grid")
 
 
 def marching_tetrahedra(points, tets, sdf, staged=False, capacities=None):

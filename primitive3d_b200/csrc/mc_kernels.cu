@@ -252,7 +252,9 @@ __device__ __forceinline__ uint32_t low_mask_clamped(int n) {
     return r - 1u;
 }
 
-template <bool TMA, typename T>
+// SPARSE: the block-sparse form (g.tile_list names the tiles to visit); a template parameter so that the dense
+// instances carry none of it
+template <bool TMA, typename T, bool SPARSE>
 __global__ void __launch_bounds__(kTileThreads, 4)
     k_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ grid, McGeom g, McWorkspace ws,
            McEmitParams prm, float *__restrict__ verts, unsigned long long vcap, int mode) {
@@ -274,7 +276,16 @@ __global__ void __launch_bounds__(kTileThreads, 4)
     auto locate = [&](uint32_t t) {
         TileCoord c;
         c.x0 = c.y0 = c.p = 0, c.tile = (int)t, c.piece_base = 0, c.pad = 0;
-        if (t < ntiles) {
+        if (SPARSE && t < ntiles) {
+            // block-sparse form: the caller's tile id, x-block major; an id past the grid is a tile without samples
+            const uint32_t id = __ldg(g.tile_list + t);
+            const uint32_t per_x = (uint32_t)g.nyb * (uint32_t)np;
+            const uint32_t xb = id / per_x, rem = id - xb * per_x;
+            const uint32_t yb = rem / np, p = rem - yb * np;
+            c.x0 = (int)(xb < (uint32_t)g.nxb ? xb * kTileX : (uint32_t)g.nxb * kTileX);
+            c.y0 = (int)(yb * kTileY), c.p = (int)p;
+            c.piece_base = ((long long)c.x0 * ry + c.y0) * np + c.p;
+        } else if (t < ntiles) {
             const uint32_t per_band = (uint32_t)g.nxb * (uint32_t)g.band * (uint32_t)np;
             const uint32_t bi = t / per_band, rem = t - bi * per_band;
             const uint32_t left = (uint32_t)g.nyb - bi * (uint32_t)g.band, cur = left < (uint32_t)g.band ? left : (uint32_t)g.band;
@@ -529,6 +540,23 @@ __global__ void __launch_bounds__(kTileThreads, 4)
             if (tid < 32 && x0 + kTileX == ox && ox < rx && y0 + (tid >> 2) < ry)
                 ws.bits[((int64_t)ox * ry + y0 + (tid >> 2)) * (4 * (int64_t)np) + 4 * p + (tid & 3)] =
                     S.sbits[(kTileX * kRowPitch + (tid >> 2)) * kSbitsStride + (tid & 3)];
+            if (SPARSE) {
+                // block-sparse form: the tiles next to this one may not be visited, yet the cells on this tile's +x /
+                // +y / +z faces read their first rows / samples.  OR the staged halo bits into the (zeroed) bit words:
+                // a neighbour that is visited writes the same bits and more.
+                if (tid < 4 * 17) {                      // halo rows: xi = 8 (nine of them), yi = 8 (eight more), 4 words
+                    const int h = tid >> 2, hw = tid & 3;
+                    const int hx_ = h < 9 ? kTileX : h - 9, hy_ = h < 9 ? h : kTileY;
+                    const int gx = x0 + hx_, gy = y0 + hy_;
+                    const uint32_t v = S.sbits[(hx_ * kRowPitch + hy_) * kSbitsStride + hw];
+                    if (gx < rx && gy < ry && v) atomicOr(ws.bits + ((int64_t)gx * ry + gy) * (4 * (int64_t)np) + 4 * p + hw, v);
+                } else if (tid >= 128 && tid < 128 + kBoxRows && p + 1 < np) {   // sample z0 + 128 of every staged row
+                    const int h = tid - 128, hx_ = h / kRowPitch, hy_ = h - hx_ * kRowPitch;
+                    const int gx = x0 + hx_, gy = y0 + hy_;
+                    if (gx < rx && gy < ry && (S.sbits[h * kSbitsStride + 4] & 1u))
+                        atomicOr(ws.bits + ((int64_t)gx * ry + gy) * (4 * (int64_t)np) + 4 * (p + 1), 1u);
+                }
+            }
         }
         // the look-back result of the top of this iteration: written by warp 0 before [bits], read here, and not
         // overwritten before warp 0 has passed [count]
@@ -1061,21 +1089,21 @@ bool force_generic() {
     return v;
 }
 
-template <bool TMA, typename T>
+template <bool TMA, typename T, bool SPARSE = false>
 void launch_tile_kernel(const CUtensorMap &map, const void *grid, const McGeom &g, const McWorkspace &ws,
                         const McEmitParams &p, float *verts, int64_t vcap, int mode, cudaStream_t s) {
     // every CTA must be resident: a CTA waits for tiles with lower ids, which running CTAs hold
     static int cache[kMaxDevices];
     const int per_sm = per_device(cache, [] {
-        cudaFuncSetAttribute(k_tile<TMA, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
+        cudaFuncSetAttribute(k_tile<TMA, T, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes);
         int n = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA, T>, kTileThreads, kTileSmemBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<TMA, T, SPARSE>, kTileThreads, kTileSmemBytes);
         return n > 0 ? n : 1;
     });
     const int64_t cap = (int64_t)sm_count() * per_sm;
     const unsigned blocks = (unsigned)(g.ntiles < cap ? g.ntiles : cap);
-    k_tile<TMA, T><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, static_cast<const T *>(grid), g, ws, p, verts,
-                                                                (unsigned long long)(vcap > 0 ? vcap : 0), mode);
+    k_tile<TMA, T, SPARSE><<<blocks, kTileThreads, kTileSmemBytes, s>>>(map, static_cast<const T *>(grid), g, ws, p, verts,
+                                                                        (unsigned long long)(vcap > 0 ? vcap : 0), mode);
 }
 
 }  // namespace
@@ -1108,6 +1136,12 @@ void launch_tile_pass(const void *grid, int dtype, const McGeom &g, const McWork
                 return;
             }
         }
+    }
+    if (g.tile_list) {  // block-sparse form: float32 grids
+        if (dtype != 0) g_tile_error = "the block-sparse form takes float32 grids";
+        else if (tma) launch_tile_kernel<true, float, true>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
+        else launch_tile_kernel<false, float, true>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);
+        return;
     }
     if (tma) {
         launch_tile_kernel<true, float>(map, grid, g, ws, p, verts, vertex_capacity, mode, s);

@@ -57,6 +57,9 @@ struct McGeom {
     int64_t nrounds;      // ceil(ntiles / 256): rounds of the tile scan
     int64_t nfrounds;     // ceil(nchunks / 256): rounds of face chunks
     uint64_t magic_np;    // floor(2^64 / np) + 1: n / np == umul64hi(n, magic_np) for n < 2^32 (np > 1)
+    // block-sparse form (p3d_mc_extract_sparse): the tile pass visits only these tiles, in this order (ntiles = their
+    // number), ids = (x-block * nyb + y-block) * np + piece; nullptr = every tile, in band order
+    const uint32_t *tile_list;
 };
 
 // Workspace header (device).  Zeroed before every count.

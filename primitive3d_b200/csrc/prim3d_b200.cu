@@ -60,6 +60,7 @@ bool make_geom(const p3d_mc_desc *d, p3d::McGeom *g) {
     g->nrounds = (g->ntiles + p3d::kRoundTiles - 1) / p3d::kRoundTiles;
     g->nfrounds = (g->nchunks + p3d::kRoundTiles - 1) / p3d::kRoundTiles;
     g->magic_np = g->np > 1 ? ~0ull / (uint64_t)g->np + 1 : 0;
+    g->tile_list = nullptr;
     if (g->ntiles > ((int64_t)1 << 31) || d->rx * d->ry * (int64_t)g->np > ((int64_t)1 << 40)) return false;
     return true;
 }
@@ -354,6 +355,47 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
     counts_host[1] = dst[1];
     if (counts_host[0] > INT32_MAX)
         return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract: vertex count exceeds the int32 face-index contract");
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_extract_sparse(const p3d_mc_desc *desc, const void *grid, int dtype, const uint32_t *tiles, int64_t num_tiles,
+                                 void *workspace, size_t workspace_bytes, float *vertices, int64_t vertex_capacity, int32_t *faces,
+                                 int64_t face_capacity, int64_t *counts_host, void *stream) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g)) return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: invalid descriptor");
+    if (dtype != P3D_F32) return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: float32 grids only");
+    if (!grid || !workspace || !counts_host || num_tiles < 0 || (num_tiles > 0 && !tiles))
+        return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: null pointer or negative tile count");
+    if (desc->global_rx < 1 || desc->rx != desc->owned_x) return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: whole grids only");
+    if (num_tiles > g.ntiles) return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: more tiles listed than the grid has");
+    if (vertex_capacity < 0 || (vertex_capacity > 0 && !vertices) || face_capacity < 0 || (face_capacity > 0 && !faces))
+        return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: capacity without a buffer");
+    const Layout l = make_layout(g);  // sized for the dense grid: the per-piece tables are indexed by position
+    if (workspace_bytes < l.total) return fail(P3D_ERR_WORKSPACE, "p3d_mc_extract_sparse: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % kAlign) return fail(P3D_ERR_INVALID, "p3d_mc_extract_sparse: workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const p3d::McWorkspace ws = bind(workspace, l);
+    // the tables and bit words of the tiles that are NOT visited must read as "nothing here": everything is zeroed
+    P3D_CUDA(cudaMemsetAsync(workspace, 0, l.total, s));
+    counts_host[0] = counts_host[1] = 0;
+    if (num_tiles == 0) return P3D_OK;
+    p3d::McGeom gs = g;       // the tile pass walks the list (its scan runs over list positions) ...
+    gs.tile_list = tiles;
+    gs.ntiles = num_tiles;
+    gs.nrounds = (num_tiles + p3d::kRoundTiles - 1) / p3d::kRoundTiles;
+    p3d::launch_tile_pass(grid, dtype, gs, ws, make_params(desc, 0), vertices, vertex_capacity, 0, s);
+    if (p3d::tile_pass_error()) return fail(P3D_ERR_CUDA, std::string("p3d_mc_extract_sparse: ") + p3d::tile_pass_error());
+    // ... the face pass walks every row of the grid: pieces without triangles cost it a count word each
+    if (faces) p3d::launch_faces(g, ws, make_params(desc, 0), faces, face_capacity, false, s);
+    P3D_CUDA(cudaGetLastError());
+    int64_t *pin = pinned_counts();
+    int64_t *dst = pin ? pin : counts_host;
+    P3D_CUDA(cudaMemcpyAsync(dst, &ws.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaStreamSynchronize(s));
+    counts_host[0] = dst[0];
+    counts_host[1] = dst[1];
+    if (counts_host[0] > INT32_MAX)
+        return fail(P3D_ERR_OVERFLOW, "p3d_mc_extract_sparse: vertex count exceeds the int32 face-index contract");
     return P3D_OK;
 }
 

@@ -20,7 +20,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ["p3d_mc_workspace_bytes", "p3d_mc_vertex_capacity_hint", "p3d_mc_count", "p3d_mc_vertices", "p3d_mc_faces",
-              "p3d_mc_count_typed", "p3d_mc_vertices_typed", "p3d_mc_extract", "p3d_mc_extract_batch", "p3d_mc_batch_workspace_bytes", "p3d_mc_extract_host",
+              "p3d_mc_count_typed", "p3d_mc_vertices_typed", "p3d_mc_extract", "p3d_mc_extract_sparse", "p3d_mc_extract_batch", "p3d_mc_batch_workspace_bytes", "p3d_mc_extract_host",
               "p3d_mc_extract_host_arena_bytes", "p3d_mc_tile_async", "p3d_mc_exchange_words", "p3d_mc_export_exchange",
               "p3d_mc_faces_exchanged", "p3d_mc_sharded_extract", "p3d_ply_pack",
               "p3d_mc_run", "p3d_mc_plane_table_words", "p3d_mc_export_first_plane",

@@ -268,6 +268,57 @@ def test_host_shard_uploaded_in_overlapped_parts(shape, parts, dtype):
     assert not m2.vertices.is_cuda and torch.equal(m2.vertices, m.vertices.cpu()) and torch.equal(m2.faces, m.faces.cpu())
 
 
+@pytest.mark.parametrize("name", ["bunny66", "sphere128", "gyroid128", "noise33_s0", "noise_long_rows", "noncubic", "thin_z",
+                                  "bounds_asym", "waves_rows_np8", "empty", "full"])
+def test_block_sparse_form_equals_the_dense_call(name):
+    """p3d_mc_extract_sparse over the tiles that hold the surface gives the dense call's mesh (faces in the same
+    voxel-major order; vertices numbered in list order): with the minimal list, with the list reversed, with every
+    tile of the grid listed, and with an id past the grid thrown in."""
+    from primitive3d_b200 import capi
+    make, thresh, lower, upper = CASES[name]
+    grid_np = np.ascontiguousarray(make())
+    g = torch.from_numpy(grid_np).cuda()
+    v0, f0 = capi.marching_cubes(g, thresh, lower, upper)
+    v0, f0 = v0.cpu().numpy(), f0.cpu().numpy()
+    tiles = capi.active_tiles(g, thresh)
+    nxb, nyb, npz = -(-g.shape[0] // 8), -(-g.shape[1] // 8), -(-g.shape[2] // 128)
+    every = torch.arange(nxb * nyb * npz, dtype=torch.int32, device="cuda")
+    assert tiles.numel() <= every.numel()
+    if name in ("empty", "full"):
+        assert tiles.numel() == 0
+    lists = [tiles, tiles.flip(0).contiguous(), every]
+    if tiles.numel() < every.numel():
+        lists.append(torch.cat([tiles, torch.tensor([nxb * nyb * npz + 5], dtype=torch.int32, device="cuda")]))
+    for tl in lists:
+        v, f = capi.marching_cubes_sparse(g, thresh, tl, lower, upper)
+        torch.cuda.synchronize()
+        assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), v0, f0, ordered_faces=True)
+    # capacities that are too small: the counts come back and the wrapper calls again
+    v, f = capi.marching_cubes_sparse(g, thresh, tiles, lower, upper, vertex_capacity=3, face_capacity=2)
+    assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), v0, f0, ordered_faces=True)
+
+
+def test_block_sparse_form_reads_only_the_listed_tiles():
+    """Samples outside the listed tiles (and their one-sample halo) are never looked at: poison them."""
+    from primitive3d_b200 import capi
+    grid_np = inputs.sphere_int64(200).astype(np.float32)
+    g = torch.from_numpy(np.ascontiguousarray(grid_np)).cuda()
+    v0, f0 = capi.marching_cubes(g, 0.0)
+    tiles = capi.active_tiles(g, 0.0)
+    nxb, nyb, npz = -(-200 // 8), -(-200 // 8), -(-200 // 128)
+    keep = torch.zeros((nxb, nyb, npz), dtype=torch.bool, device="cuda").view(-1)
+    keep[tiles.long()] = True
+    keep = keep.view(nxb, 1, nyb, 1, npz, 1).expand(nxb, 8, nyb, 8, npz, 128).reshape(nxb * 8, nyb * 8, npz * 128)
+    near = keep.clone()                      # listed tiles plus one sample towards +x, +y, +z
+    near[1:] |= keep[:-1]
+    near[:, 1:] |= near[:, :-1].clone()
+    near[:, :, 1:] |= near[:, :, :-1].clone()
+    poisoned = torch.where(near[:200, :200, :200], g, torch.full_like(g, float("nan")))
+    assert tiles.numel() < 0.5 * nxb * nyb * npz
+    v, f = capi.marching_cubes_sparse(poisoned, 0.0, tiles)
+    assert_same_mesh(v.cpu().numpy(), f.cpu().numpy(), v0.cpu().numpy(), f0.cpu().numpy(), ordered_faces=True)
+
+
 def test_batched_small_grids_equal_one_by_one():
     """p3d_mc_extract_batch: many small grids queued back to back, one host wait; every mesh equals the one the
     single call gives (including a grid dense enough to overflow its speculative buffers, and an empty one)."""
