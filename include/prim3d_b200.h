@@ -136,11 +136,15 @@ p3d_status p3d_mc_vertices_typed(const p3d_mc_desc *desc, const void *grid, int 
 p3d_status p3d_mc_faces(const p3d_mc_desc *desc, const void *workspace, int32_t *faces,
                         int64_t vertex_id_base, void *stream);
 
-/* 1 if p3d_mc_extract handles this grid by its single-launch path (small float32 grids: one kernel for the whole
- * extraction instead of the tiled passes; off unless the environment sets P3D_MC_SMALL_SINGLE_MAX = samples, because
- * for ONE grid it measured no faster than the tiled passes -- batches are where it pays, p3d_mc_extract_batch), else 0.  After a single-launch extraction the workspace does NOT hold the
+/* 1 if p3d_mc_extract handles this grid by its single-launch path (float32 grids of up to P3D_MC_SMALL_SINGLE_MAX
+ * samples, default 2^20: one kernel for the whole extraction instead of the tiled passes' launch chain -- 36 us
+ * against 56 us per call at the reference's bunny 66^3 example; 0 in the environment variable sends every single grid
+ * through the tiled passes), else 0.  Vertices are then numbered voxel-major by (row, 32-sample word) instead of tile
+ * by tile (the same mesh, other ids), and after such an extraction the workspace does NOT hold the
  * state p3d_mc_vertices / p3d_mc_faces continue from: an output that did not fit its capacity is redone by calling
- * p3d_mc_extract again with an exact buffer for it (capacity 0 for the output that did fit). */
+ * p3d_mc_extract again with an exact buffer for it (capacity 0 for the output that did fit).  The path keeps two
+ * barrier words per host thread and device in memory the library owns: a host thread's calls must not overlap, which
+ * they cannot, since p3d_mc_extract and p3d_mc_extract_batch return after their one stream wait. */
 int p3d_mc_single_launch(const p3d_mc_desc *desc, int dtype);
 
 /* Whole extraction with ONE host synchronisation (single GPU: owned_x == rx).  Both passes are

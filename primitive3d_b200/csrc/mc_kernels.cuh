@@ -136,10 +136,9 @@ struct SmallBatch {
     int32_t ngrids;
     SmallGrid g0;             // the grid itself when ngrids == 1 (no descriptor array in device memory)
 };
-struct SmallHeader {          // zeroed before the launch
+struct SmallHeader {          // written by the launch (no zeroing needed)
     unsigned long long total_v, total_f;
-    unsigned int barrier;
-    unsigned int pad[3];
+    unsigned int pad[4];
 };
 struct SmallWorkspace {
     SmallHeader *header;
@@ -148,10 +147,15 @@ struct SmallWorkspace {
     uint4 *corner;                  // [nwords] inside bits {a, b, c, d} of the four rows of a word's cells
     uint32_t *cnt;                  // [nwords] nx | ny << 6 | nz << 12 | nf << 18 | next bits << 28
     uint2 *first;                   // [nwords] batch-wide first vertex id / first face index of a word
+    unsigned int *sync;             // {barrier arrivals, exits}: library-owned, zero between launches (set by launch_small)
 };
 size_t small_workspace_bytes(int64_t nwords, int ngrids);
 SmallWorkspace bind_small(void *base, int64_t nwords, int ngrids, SmallGrid **grids_dev);
-void launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWorkspace &ws, cudaStream_t s);
+// totals_host: optional pinned, device-visible landing place of the batch totals {V, F}.  The caller must wait for the
+// stream before the same host thread launches again (the barrier words are per host thread and device); returns false
+// if those words could not be allocated.
+bool launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWorkspace &ws, cudaStream_t s,
+                  unsigned long long *totals_host);
 
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor
 

@@ -127,14 +127,18 @@ int64_t small_max_samples() {
     return v;
 }
 
-// A single grid goes through the single-launch kernel only on request (P3D_MC_SMALL_SINGLE_MAX = samples): measured on
-// B200 its one launch (37 us at bunny 66^3: three latency-bound phases and two device-wide barriers) is no faster
-// than the tiled passes' five (35 us), so the default keeps one numbering for every single-grid entry point.  A
-// BATCH of small grids is where the single launch pays: 64 x 66^3 in 1.0 ms against 3.9 ms one by one.
+// A single grid of up to P3D_MC_SMALL_SINGLE_MAX samples (default 2^20, about 100^3) goes through the single-launch kernel:
+// measured on B200 through the pybind module, bunny 66^3 costs 36 us per call there against 56 us for the tiled passes'
+// launch chain (kernel 22 us; no memset node before it, no copy node behind it); at 128^3 the two are level (sphere: 66
+// against 59 us, gyroid: 97 against 98 us), above that the tiled passes win.  0 sends every single grid through the
+// tiled passes (one vertex numbering for all sizes).
+#ifndef P3D_MC_SMALL_SINGLE_MAX_DEFAULT
+#define P3D_MC_SMALL_SINGLE_MAX_DEFAULT (1 << 20)
+#endif
 int64_t small_single_max_samples() {
     static const int64_t v = [] {
         const char *e = getenv("P3D_MC_SMALL_SINGLE_MAX");
-        return e ? (int64_t)atoll(e) : (int64_t)0;
+        return e ? (int64_t)atoll(e) : (int64_t)P3D_MC_SMALL_SINGLE_MAX_DEFAULT;
     }();
     return v;
 }
@@ -170,7 +174,7 @@ int64_t *pinned_counts(size_t pairs = 1) {
     if (pairs > cap) {
         if (buf) cudaFreeHost(buf);
         cap = pairs < 64 ? 64 : pairs * 2;
-        if (cudaHostAlloc(reinterpret_cast<void **>(&buf), cap * 2 * sizeof(int64_t), cudaHostAllocPortable) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&buf), cap * 2 * sizeof(int64_t), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
             buf = nullptr;
             cap = 0;
         }
@@ -329,14 +333,15 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
         p3d::SmallBatch b;
         b.nwords = small_words(desc), b.ngrids = 1;
         b.g0 = small_grid(desc, grid, vertices, vertex_capacity, faces, face_capacity, 0);
-        P3D_CUDA(cudaMemsetAsync(sw.header, 0, sizeof(p3d::SmallHeader), s));
-        p3d::launch_small(b, nullptr, sw, s);
-        P3D_CUDA(cudaGetLastError());
+        // the kernel writes {V, F} straight into the pinned landing pad (mapped into the device's address space): no
+        // memset node before it, no copy node behind it; the host reads the counts as soon as the stream is idle
         int64_t *pin = pinned_counts();
-        int64_t *dst = pin ? pin : counts_host;
-        P3D_CUDA(cudaMemcpyAsync(dst, &sw.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (!p3d::launch_small(b, nullptr, sw, s, reinterpret_cast<unsigned long long *>(pin)))
+            return fail(P3D_ERR_CUDA, "p3d_mc_extract: no memory for the barrier words");
+        P3D_CUDA(cudaGetLastError());
+        if (!pin) P3D_CUDA(cudaMemcpyAsync(counts_host, &sw.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         P3D_CUDA(cudaStreamSynchronize(s));
-        counts_host[0] = dst[0], counts_host[1] = dst[1];
+        if (pin) counts_host[0] = pin[0], counts_host[1] = pin[1];
         return P3D_OK;
     }
     const p3d::McWorkspace ws = bind(workspace, l);
@@ -451,9 +456,9 @@ p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, con
             p3d::SmallBatch b;
             b.nwords = words, b.ngrids = (int32_t)num_grids;
             b.g0 = stage[0];
-            P3D_CUDA(cudaMemsetAsync(sw.header, 0, sizeof(p3d::SmallHeader), s));
             P3D_CUDA(cudaMemcpyAsync(grids_dev, stage, (size_t)num_grids * sizeof(p3d::SmallGrid), cudaMemcpyHostToDevice, s));
-            p3d::launch_small(b, grids_dev, sw, s);
+            if (!p3d::launch_small(b, grids_dev, sw, s, nullptr))
+                return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: no memory for the barrier words");
             P3D_CUDA(cudaGetLastError());
             // per-grid counts = differences of the grids' bases (the batch totals close the last one)
             std::vector<int64_t> base(2 * (size_t)num_grids);

@@ -342,7 +342,7 @@ def test_batched_small_grids_equal_one_by_one():
 @pytest.mark.parametrize("name", list(CASES))
 def test_one_call_extraction_matches_oracle(name):
     """p3d_mc_extract, the entry prim3d.libPrim3D.marching_cubes sits on (the tiled passes, or the single-launch kernel
-    of mc_small.cu when P3D_MC_SMALL_SINGLE_MAX asks for it: tests/test_mc_cuda.py::test_single_launch_kernel_matches_oracle).
+    of mc_small.cu for grids of up to P3D_MC_SMALL_SINGLE_MAX samples; test_single_launch_kernel_matches_oracle runs every case through that kernel).
     Against the oracle, triangle by triangle."""
     from primitive3d_b200 import capi
     make, thresh, lower, upper = CASES[name]
@@ -388,8 +388,8 @@ def test_one_launch_for_a_batch_of_small_grids():
 
 
 def test_small_path_switch(monkeypatch):
-    """P3D_MC_SMALL_SINGLE_MAX sends single small grids through the single-launch kernel (off by default: for one
-    grid it is no faster than the tiled passes): same mesh as the tiled passes give."""
+    """P3D_MC_SMALL_SINGLE_MAX decides which single grids go through the single-launch kernel (default: up to 2^20
+    samples; 0: none): same mesh as the tiled passes give, another vertex numbering."""
     import subprocess
     import sys
     code = ("import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"

@@ -3,8 +3,8 @@
 (CUDA events around back-to-back calls, so launch overhead and the one host wait are inside), and a batch of 64
 bunny-sized grids in one launch (p3d_mc_extract_batch) against the same grids one by one.
 
-  python tools/prof_small.py            # single-launch path (default)
-  P3D_MC_SMALL_MAX=0 python tools/prof_small.py   # the tiled passes for comparison
+  python tools/prof_small.py                             # defaults (single grids of up to 2^20 samples in one launch)
+  P3D_MC_SMALL_SINGLE_MAX=0 python tools/prof_small.py   # single grids through the tiled passes, for comparison
 """
 import json
 import os
