@@ -271,8 +271,15 @@ def marching_cubes_batch(grids, thresh, lower=None, upper=None):
     if any(_grid_ok(g) != dtype or g.device != dev for g in grids):
         raise ValueError("a batch must have one dtype and one device")
     n = len(grids)
-    descs = (McDesc * n)(*[McDesc.make(g.shape, thresh, lower, upper) for g in grids])
-    sizes = [_desc_sizes(d) for d in descs]
+    # one descriptor and one size query per distinct shape (the host side of a batch of small grids costs as much as
+    # its one kernel launch: everything per grid is kept to a few Python operations)
+    by_shape = {}
+    for g in grids:
+        if g.shape not in by_shape:
+            d = McDesc.make(g.shape, thresh, lower, upper)
+            by_shape[g.shape] = (d, _desc_sizes(d))
+    descs = (McDesc * n)(*[by_shape[g.shape][0] for g in grids])
+    sizes = [by_shape[g.shape][1] for g in grids]
     ws = torch.empty(max(max(s[0] for s in sizes), lib().p3d_mc_batch_workspace_bytes(n, descs)), dtype=torch.uint8, device=dev)
     vcaps, fcaps = [s[1] for s in sizes], [2 * s[1] for s in sizes]
     # one allocation per output kind, carved into per-grid buffers (256-byte aligned starts)
@@ -291,11 +298,13 @@ def marching_cubes_batch(grids, thresh, lower=None, upper=None):
                                          ptrs([vall.data_ptr() + o for o in voff[:-1]]), i64s(vcaps),
                                          ptrs([fall.data_ptr() + o for o in foff[:-1]]), i64s(fcaps), counts, _stream()))
     out = []
+    vall32, fall32 = vall.view(torch.float32), fall.view(torch.int32)
+    counts = list(counts)
     for i, g in enumerate(grids):
         V, F = counts[2 * i], counts[2 * i + 1]
         if V <= vcaps[i] and F <= fcaps[i]:
-            v = vall[voff[i]:voff[i] + 12 * V].view(torch.float32).view(V, 3)
-            f = fall[foff[i]:foff[i] + 12 * F].view(torch.int32).view(F, 3)
+            v = torch.as_strided(vall32, (V, 3), (3, 1), voff[i] // 4)
+            f = torch.as_strided(fall32, (F, 3), (3, 1), foff[i] // 4)
         else:
             v, f, _, _ = mc_extract(descs[i], g, V, F)
         out.append((v, f))

@@ -13,7 +13,7 @@ timeout 600 ncu $full -k regex:"k_tile|k_faces" -c 2 -o $out/${tag}_mc1024 -f py
 # ... and the 8-GPU shard of gyroid 2048^3 (257 planes of 2048^2: tile pass, chunk form of the face pass)
 timeout 600 ncu $full -k regex:"k_tile|k_faces" -c 2 -o $out/${tag}_mc2048slab -f python tools/prof_mc.py --size 2048 --planes 257 --reps 1 > $out/${tag}_prof_mc2048slab.log 2>&1
 # the single-launch kernel for small grids (bunny 66^3) and a batch of them
-timeout 300 env P3D_MC_SMALL_SINGLE_MAX=4194304 ncu $full -k regex:k_small -c 2 -o $out/${tag}_small -f python tools/prof_small.py > $out/${tag}_prof_small.log 2>&1
+timeout 300 ncu $full -k regex:k_small --launch-skip 3 -c 2 -o $out/${tag}_small -f python tools/prof_small_kernel.py both > $out/${tag}_prof_small.log 2>&1
 # marching tetrahedra, Kuhn 128^3: the second call (capacities remembered) of the one-call path, then the staged kernels
 timeout 300 ncu $full -k regex:k_mtx --launch-skip 5 -c 5 -o $out/${tag}_mtx -f python tools/prof_mt.py 128 0 > $out/${tag}_prof_mtx.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_mt|k_sort" -c 40 --csv --log-file $out/${tag}_launches_tets.csv \
@@ -22,4 +22,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 timeout 300 python tools/prof_mc.py --size 1024 > $out/${tag}_kernel_times.json 2> $out/${tag}_kernel_times.err
 timeout 120 python tools/prof_mt.py 128 30 > $out/${tag}_tets_time.log 2>&1
 timeout 200 python tools/prof_small.py > $out/${tag}_small_times.json 2> $out/${tag}_small_times.err
+timeout 200 env P3D_MC_SMALL_SINGLE_MAX=0 python tools/prof_small.py > $out/${tag}_small_times_tiled.json 2>> $out/${tag}_small_times.err
+timeout 200 python tools/prof_call_overhead.py > $out/${tag}_call_overhead.json 2>> $out/${tag}_small_times.err
 ls -la $out | grep ${tag}_ | head -40

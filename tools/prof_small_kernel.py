@@ -4,6 +4,8 @@
   python tools/prof_small_kernel.py single   # bunny 66^3 through p3d_mc_extract, 3 calls
   python tools/prof_small_kernel.py batch    # 64 bunny-sized grids in one launch, 2 calls
   python tools/prof_small_kernel.py floor    # us per call of a 4^3 grid (launch + host wait + wrapper) and of bunny 66^3
+  python tools/prof_small_kernel.py both     # single, single, batch, single, batch: `ncu --launch-skip 3 -c 2` captures
+                                             # one warm launch of each kind (tools/collect_profiles.sh)
 """
 import json
 import os
@@ -26,6 +28,13 @@ def main():
     if mode == "single":
         for _ in range(3):
             prim3d._C.marching_cubes(bunny, 0.0, [0, 0, 0], [66.0] * 3)
+    elif mode == "both":
+        batch = [bunny * (1.0 + 0.01 * i) for i in range(64)]
+        for kind in "ssbsb":
+            if kind == "s":
+                prim3d._C.marching_cubes(bunny, 0.0, [0, 0, 0], [66.0] * 3)
+            else:
+                capi.marching_cubes_batch(batch, 0.0)
     elif mode == "batch":
         batch = [bunny * (1.0 + 0.01 * i) for i in range(64)]
         for _ in range(2):
