@@ -152,8 +152,9 @@ struct SmallWorkspace {
 size_t small_workspace_bytes(int64_t nwords, int ngrids);
 SmallWorkspace bind_small(void *base, int64_t nwords, int ngrids, SmallGrid **grids_dev);
 // totals_host: optional pinned, device-visible landing place of the batch totals {V, F}.  The caller must wait for the
-// stream before the same host thread launches again (the barrier words are per host thread and device); returns false
-// if those words could not be allocated.
+// stream before the same host thread launches again (the barrier words are per host thread and device); a cooperative
+// launch, so that launches of several host threads cannot starve each other of SMs at the barrier.  Returns false if
+// the barrier words could not be allocated or the launch was refused.
 bool launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWorkspace &ws, cudaStream_t s,
                   unsigned long long *totals_host);
 

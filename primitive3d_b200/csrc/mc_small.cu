@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         const int64_t mine = c0 + lane;
         uint32_t packed = 0;
         if (lane < n) packed = ws.cnt[mine];
-        const uint32_t my_nx = packed & 63u, my_ny = (packed >> 6) & 63u, my_nf = (packed >> 18) & 1023u;
+        const uint32_t my_nf = (packed >> 18) & 1023u;
         const bool busy = (packed & 0x0fffffffu) != 0u;
         uint32_t my_A = 0, my_B = 0, my_C = 0, my_D = 0, my_vlocal = 0, my_flocal = 0;
         uint32_t my_by = 0, my_bz = 0, my_cz = 0, my_dx = 0, my_dz = 0, my_n4 = 0, my_n5 = 0, my_n6 = 0, my_n7 = 0;
@@ -488,8 +488,21 @@ bool launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWo
     int64_t group = (b.nwords + ctas * kSmallWarps - 1) / (ctas * kSmallWarps);
     group = group < 2 ? 2 : (group > 32 ? 32 : group);
     if (group_env >= 1 && group_env <= 32) group = group_env;
-    k_small<<<(unsigned)ctas, kSmallThreads, 0, s>>>(b, grids_dev, ws, totals_host, (int)group);
-    return true;
+    // A cooperative launch: the device-wide barrier needs every CTA resident at once, and only the driver can promise
+    // that when another stream (another host thread's k_small, say) competes for the SMs -- two plain launches could
+    // each hold half of the SMs and wait for the other half for ever.
+    static const bool plain = [] {
+        const char *e = getenv("P3D_SMALL_PLAIN_LAUNCH");  // tuning runs only
+        return e && atoi(e) != 0;
+    }();
+    int group_i = (int)group;
+    if (plain) {
+        k_small<<<(unsigned)ctas, kSmallThreads, 0, s>>>(b, grids_dev, ws, totals_host, group_i);
+        return true;
+    }
+    void *args[] = {const_cast<SmallBatch *>(&b), &grids_dev, &ws, &totals_host, &group_i};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_small), dim3((unsigned)ctas), dim3(kSmallThreads), args, 0, s) ==
+           cudaSuccess;
 }
 
 }  // namespace p3d

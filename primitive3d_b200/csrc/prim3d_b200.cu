@@ -337,7 +337,7 @@ p3d_status p3d_mc_extract(const p3d_mc_desc *desc, const void *grid, int dtype, 
         // memset node before it, no copy node behind it; the host reads the counts as soon as the stream is idle
         int64_t *pin = pinned_counts();
         if (!p3d::launch_small(b, nullptr, sw, s, reinterpret_cast<unsigned long long *>(pin)))
-            return fail(P3D_ERR_CUDA, "p3d_mc_extract: no memory for the barrier words");
+            return fail(P3D_ERR_CUDA, "p3d_mc_extract: the single-launch kernel could not be launched (barrier words or cooperative launch)");
         P3D_CUDA(cudaGetLastError());
         if (!pin) P3D_CUDA(cudaMemcpyAsync(counts_host, &sw.header->total_v, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         P3D_CUDA(cudaStreamSynchronize(s));
@@ -458,7 +458,7 @@ p3d_status p3d_mc_extract_batch(int64_t num_grids, const p3d_mc_desc *descs, con
             b.g0 = stage[0];
             P3D_CUDA(cudaMemcpyAsync(grids_dev, stage, (size_t)num_grids * sizeof(p3d::SmallGrid), cudaMemcpyHostToDevice, s));
             if (!p3d::launch_small(b, grids_dev, sw, s, nullptr))
-                return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: no memory for the barrier words");
+                return fail(P3D_ERR_CUDA, "p3d_mc_extract_batch: the single-launch kernel could not be launched (barrier words or cooperative launch)");
             P3D_CUDA(cudaGetLastError());
             // per-grid counts = differences of the grids' bases (the batch totals close the last one)
             std::vector<int64_t> base(2 * (size_t)num_grids);

@@ -407,6 +407,41 @@ def test_small_path_switch(monkeypatch):
     assert_same_mesh(outs[0]["v"], outs[0]["f"], outs[1]["v"], outs[1]["f"], ordered_faces=True)   # ... of one mesh
 
 
+def test_small_grids_from_two_host_threads_at_once():
+    """Two host threads extract small grids on their own streams at the same time: the single-launch kernel spans the
+    device with a barrier inside, so its launches are cooperative (two plain launches could each hold half of the SMs
+    and wait for the other half) and its barrier words are per host thread.  Run in a child process under a timeout:
+    a deadlock must fail this test, not hang the suite."""
+    import subprocess
+    import sys
+    code = """
+import sys, threading
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from oracle import inputs
+from primitive3d_b200 import capi
+grids = [torch.from_numpy(inputs.noise((40, 36, 70), 5 + i)).cuda() for i in range(2)]
+want = [capi.mc_extract(capi.McDesc.make(g.shape, 0.0), g) for g in grids]
+torch.cuda.synchronize()
+bad = []
+def work(i):
+    with torch.cuda.stream(torch.cuda.Stream()):
+        desc = capi.McDesc.make(grids[i].shape, 0.0)
+        for _ in range(300):
+            v, f, V, F = capi.mc_extract(desc, grids[i])
+            if (V, F) != want[i][2:] or not torch.equal(f, want[i][1]) or not torch.equal(v.view(torch.int32), want[i][0].view(torch.int32)):
+                bad.append(i)
+                return
+ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+[t.start() for t in ts]; [t.join() for t in ts]
+torch.cuda.synchronize()
+assert not bad, bad
+print("ok")
+""" % (os.path.dirname(HERE), HERE)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_unsupported_dtype_is_cast_by_the_wrapper():
     import prim3d
     g = torch.from_numpy(inputs.noise((12, 12, 12), 26)).cuda()
