@@ -176,7 +176,7 @@ extern "C" p3d_status p3d_mc_extract_host(const p3d_mc_desc *desc, const void *h
 
     Plan pl;
     if (!make_plan(desc, dtype, slab_planes, &pl)) return p3d::set_error(P3D_ERR_INVALID, "p3d_mc_extract_host: invalid grid shape");
-    const int64_t rx = desc->rx, plane = desc->ry * desc->rz;
+    const int64_t plane = desc->ry * desc->rz;
     slab_planes = pl.slab_planes;
     const int nslabs = pl.nslabs;
     const size_t ws_bytes = pl.ws_bytes;

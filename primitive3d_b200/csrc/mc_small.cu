@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
         const float *my_pa = nullptr;
         int my_sx = 0, my_sy = 0, my_left = 0;   // element offsets to row (x + 1, y) / (x, y + 1) (0: the row does not exist); samples from z0 on
         float my_th = 0.0f;
-        uint32_t my_zv = 0;
+        uint32_t my_zv = 0, nb = 0;
         if (lane < n) {
             const SmallGrid *gr;
             const WordGeom wg = locate_word(b, grids, c0 + lane, gr);
@@ -168,33 +168,39 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
             my_left = gr->rz - 32 * wg.w;
             my_th = gr->thresh;
             my_zv = low_mask_small(my_left - 1);  // samples with z + 1 < rz
+            // the sample after my word's 32 in each of the four rows (bit 0 of the next word), read by the word's owner:
+            // four independent loads per lane, in flight together with the rounds below.  bit 0 = row a, 1 = b, 2 = c, 3 = d
+            if (my_left > 32) {
+                const float na = __ldg(my_pa + 32);
+                const float nbv = my_sx ? __ldg(my_pa + my_sx + 32) : my_th;
+                const float nd = my_sy ? __ldg(my_pa + my_sy + 32) : my_th;
+                const float nc = my_sx && my_sy ? __ldg(my_pa + my_sx + my_sy + 32) : my_th;
+                nb = (na > my_th ? 1u : 0u) | (nbv > my_th ? 2u : 0u) | (nc > my_th ? 4u : 0u) | (nd > my_th ? 8u : 0u);
+            }
         }
-        uint32_t A = 0, B = 0, C = 0, D = 0, nb = 0;
-        // inside bits (value > thresh, :25) of the 32 samples of a word in the four rows its cells touch, and of the
-        // sample after them (bit 0 of the next word): lane i reads sample i of each row, lanes 0..3 the next sample of
-        // rows a, b, c, d.  Samples outside the grid count as outside the surface; their masks are cut by the validity
-        // tests below.  All loads of a round of words are independent: the latency is paid once per round.
+        uint32_t A = 0, B = 0, C = 0, D = 0;
+        // inside bits (value > thresh, :25) of the 32 samples of a word in the four rows its cells touch: lane i reads
+        // sample i of each row.  Samples outside the grid count as outside the surface; their masks are cut by the
+        // validity tests below.  All loads of a round of words are independent: the latency is paid once per round.
+        const int my_pack = my_sy | ((my_left > 32 ? 32 : my_left) << 24);  // sy < 2^22 (a grid has at most 4 Mi samples)
+        const bool one_grid = b.ngrids == 1;
+        const float th_one = grids[0].thresh;
 #pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const float *pa = reinterpret_cast<const float *>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_pa), j));
-            const int sx = __shfl_sync(kFull, my_sx, j), sy = __shfl_sync(kFull, my_sy, j), left = __shfl_sync(kFull, my_left, j);
-            const float th = __shfl_sync(kFull, my_th, j);
-            float va = th, vb = th, vc = th, vd = th, vn = th;
+            const int sx = __shfl_sync(kFull, my_sx, j), pack = __shfl_sync(kFull, my_pack, j);
+            const int sy = pack & 0xffffff, left = pack >> 24;
+            const float th = one_grid ? th_one : __shfl_sync(kFull, my_th, j);
+            float va = th, vb = th, vc = th, vd = th;
             if (lane < left) {
                 va = __ldg(pa + lane);
                 if (sx) vb = __ldg(pa + sx + lane);
                 if (sy) vd = __ldg(pa + sy + lane);
                 if (sx && sy) vc = __ldg(pa + sx + sy + lane);
             }
-            if (left > 32 && lane < 4) {
-                const int off = (lane == 1 || lane == 2 ? sx : 0) + (lane >= 2 ? sy : 0);
-                const bool have = lane == 0 || (lane == 1 && sx) || (lane == 2 && sx && sy) || (lane == 3 && sy);
-                if (have) vn = __ldg(pa + off + 32);
-            }
             const uint32_t a = __ballot_sync(kFull, va > th), bb = __ballot_sync(kFull, vb > th);
             const uint32_t cc = __ballot_sync(kFull, vc > th), d = __ballot_sync(kFull, vd > th);
-            const uint32_t nn = __ballot_sync(kFull, vn > th) & 15u;  // bit 0 = row a, 1 = b, 2 = c, 3 = d
-            if (lane == j) A = a, B = bb, C = cc, D = d, nb = nn;
+            if (lane == j) A = a, B = bb, C = cc, D = d;
         }
         if (lane < n) {
             const bool xin = my_sx != 0, yin = my_sy != 0;

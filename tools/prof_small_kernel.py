@@ -28,6 +28,11 @@ def main():
     if mode == "single":
         for _ in range(3):
             prim3d._C.marching_cubes(bunny, 0.0, [0, 0, 0], [66.0] * 3)
+    elif mode == "sphere128":   # with P3D_MC_SMALL_SINGLE_MAX=4194304: the single-launch kernel at 128^3
+        from primitive3d_b200 import workloads
+        g = torch.from_numpy(workloads.sphere_int64(128).astype(np.float32)).to(dev)
+        for _ in range(3):
+            prim3d._C.marching_cubes(g, 0.0, [0, 0, 0], [128.0] * 3)
     elif mode == "both":
         batch = [bunny * (1.0 + 0.01 * i) for i in range(64)]
         for kind in "ssbsb":
