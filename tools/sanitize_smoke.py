@@ -26,12 +26,13 @@ def main():
             dev = torch.from_numpy(np.ascontiguousarray(g)).cuda()
             v0, f0 = capi.marching_cubes(dev, 0.0)
             desc = capi.McDesc.make(dev.shape, 0.0)
-            v1, f1, V, F = capi.mc_extract(desc, dev)
-            assert torch.equal(v0, v1) and torch.equal(f0, f1)
+            v1, f1, V, F = capi.mc_extract(desc, dev)   # small grids: the single-launch kernel (its own vertex numbering)
+            same = lambda va, fa, vb, fb: fa.shape == fb.shape and torch.equal(va[fa.long()], vb[fb.long()])  # triangle by triangle
+            assert v0.shape == v1.shape and same(v0, f0, v1, f1)
             v2, f2 = capi.marching_cubes(dev.double(), 0.0)
             assert torch.equal(v0, v2) and torch.equal(f0, f2)
             out = capi.marching_cubes_batch([dev, dev[:, :, : shape[2] // 2].contiguous()], 0.0)
-            assert torch.equal(out[0][0], v0) and torch.equal(out[0][1], f0)
+            assert out[0][0].shape == v0.shape and same(out[0][0], out[0][1], v0, f0)
             hv, hf = capi.marching_cubes_host(torch.from_numpy(np.ascontiguousarray(g)).pin_memory(), 0.0, slab_planes=8)
             assert hv.shape == v0.shape and hf.shape == f0.shape
             torch.cuda.synchronize()
