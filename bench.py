@@ -214,8 +214,10 @@ def main():
     slab = gyroid_cuda(n, x0, x1h, dev)
     torch.cuda.synchronize()
 
-    # our kernels per step: k_tile, k_round_sums, k_faces_rows (+ k_export_exchange, k_apply_exchange on several GPUs)
-    launches_per_step = 3 if world == 1 else 5
+    # our kernels per step: k_tile, k_round_sums, k_faces_rows (+ k_export_p2p / k_export_exchange, k_wait_p2p,
+    # k_apply_exchange on several GPUs)
+    launches_per_step = 3 if world == 1 else 6
+    exchange = "nccl all-gather"
 
     if world == 1:
         # one GPU: the reference-facing module itself, prim3d.libPrim3D.marching_cubes (pybind -> p3d_mc_extract)
@@ -231,11 +233,19 @@ def main():
         if os.environ.get("P3D_BENCH_DRIVER", "c") == "python":
             def step():
                 return sharded.marching_cubes_slab(slab, 0.0, x0, n)
-        else:
+        elif os.environ.get("P3D_BENCH_EXCHANGE", "p2p") == "nccl":
             comm = sharded.nccl_comm_init()
 
             def step():
                 return sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world)
+        else:
+            # default: the same one C call with the shard-boundary exchange over peer memory (NVLink stores into the
+            # neighbours' mailboxes + flags, p3d_mc_sharded_extract_p2p): no collective call inside the timed region
+            exchange = "p2p"
+            peer = sharded.PeerExchange(slab.shape[1], slab.shape[2])
+
+            def step():
+                return sharded.marching_cubes_slab_p2p(slab, 0.0, x0, n, peer)
 
     for _ in range(args.warmup):
         out = step()
@@ -372,6 +382,11 @@ def main():
             "config": workload_config(n, world, (V_tot, F_tot)), "gpu_launches": launches_per_step * args.steps,
             "path": {"achieved_gbs": b_alg / (ms * 1e-3) / 1e9, "frac_of_peak": b_alg / (ms * 1e-3) / 1e9 / (peak * world),
                      "algorithmic_bytes": b_alg, "peak_gbs_per_gpu": peak, "peak_source": peak_src}}
+
+    if world > 1:
+        line["config"]["exchange"] = ("peer memory: NVLink stores into the neighbours' mailboxes + flags (p3d_mc_sharded_extract_p2p), "
+                                      "no collective call in the step" if exchange == "p2p" else
+                                      "one ncclAllGather of every rank's first-plane table + counts (p3d_mc_sharded_extract)")
 
     # ---- per-kernel timing on rank 0's slab (CUDA events on the launching stream) ----
     desc = capi.McDesc.make(slab.shape, 0.0, [0, 0, 0], [float(n)] * 3, owned_x=sharded.slab_range(n, world, 0)[1],

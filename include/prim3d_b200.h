@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P3D_ABI_VERSION 4
+#define P3D_ABI_VERSION 5
 
 typedef enum p3d_status {
     P3D_OK = 0,
@@ -242,6 +242,29 @@ p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int
                                   size_t workspace_bytes, void *nccl_comm, int rank, int world, uint32_t *exchange_send,
                                   uint32_t *exchange_recv, float *vertices, int64_t vertex_capacity, int32_t *faces,
                                   int64_t face_capacity, int64_t *counts_host, void *stream);
+
+/* The same one-call shard extraction with the boundary exchange over PEER MEMORY instead of a collective: every rank
+ * owns a mailbox in device memory which the other ranks of the node map through CUDA IPC; after its tile pass a rank
+ * stores its first-plane table into the mailbox of the rank below it and its {V, F} into every mailbox (NVLink /
+ * NVSwitch stores from a kernel), raises a flag, and waits for the others' flags; the face pass follows on the same
+ * stream.  No NCCL call, nothing of the payload travels to a rank that does not read it.
+ *   p3d_mc_peer_create    allocates this rank's mailbox for shards whose planes are desc's (ry x rz) and returns its
+ *                         IPC handle (p3d_mc_peer_handle_bytes() bytes) in handle_out;
+ *   p3d_mc_peer_connect   handles = the handles of ALL ranks in rank order (the caller exchanges them with whatever
+ *                         it has: MPI, torch.distributed, a file), maps the other ranks' mailboxes;
+ *   p3d_mc_sharded_extract_p2p   arguments and results as p3d_mc_sharded_extract; COLLECTIVE: every rank of the
+ *                         mailbox makes the same sequence of calls (a rank that never arrives ends the others' wait
+ *                         with P3D_ERR_CUDA after a few seconds instead of hanging the device);
+ *   p3d_mc_peer_destroy   after a barrier of the caller's: no rank may still be inside a call.
+ * One process per GPU (IPC handles cannot be opened by the process that made them); at most 32 ranks. */
+typedef struct p3d_mc_peer p3d_mc_peer;
+size_t p3d_mc_peer_handle_bytes(void);
+p3d_status p3d_mc_peer_create(const p3d_mc_desc *desc, int rank, int world, p3d_mc_peer **out, void *handle_out);
+p3d_status p3d_mc_peer_connect(p3d_mc_peer *peer, const void *handles);
+void p3d_mc_peer_destroy(p3d_mc_peer *peer);
+p3d_status p3d_mc_sharded_extract_p2p(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
+                                      size_t workspace_bytes, p3d_mc_peer *peer, float *vertices, int64_t vertex_capacity,
+                                      int32_t *faces, int64_t face_capacity, int64_t *counts_host, void *stream);
 
 /* Marching cubes of a grid in HOST memory, pipelined slab by slab on one device: while slab k is
  * extracted, slab k+1 uploads and the mesh of slab k-1 downloads, so the call costs about

@@ -19,7 +19,7 @@ BIND_SO = os.path.join(ROOT, "prim3d", "libPrim3D.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-CORE_SOURCES = ["prim3d_b200.cu", "mc_kernels.cu", "mc_faces_rows.cu", "mc_small.cu", "mt_kernels.cu", "mt_extract.cu", "ply_kernels.cu", "mc_host_stream.cu"]
+CORE_SOURCES = ["prim3d_b200.cu", "mc_kernels.cu", "mc_faces_rows.cu", "mc_small.cu", "mc_peer.cu", "mt_kernels.cu", "mt_extract.cu", "ply_kernels.cu", "mc_host_stream.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "4",
               "-Xcompiler", "-fPIC", "-ccbin", CXX]
 

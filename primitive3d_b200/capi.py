@@ -77,6 +77,15 @@ def lib():
         L.p3d_mc_sharded_extract.restype = ctypes.c_int
         L.p3d_mc_sharded_extract.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, i64, vp, i64,
                                              ctypes.POINTER(i64), vp]
+        L.p3d_mc_peer_handle_bytes.restype = sz
+        L.p3d_mc_peer_create.restype = ctypes.c_int
+        L.p3d_mc_peer_create.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), vp]
+        L.p3d_mc_peer_connect.restype = ctypes.c_int
+        L.p3d_mc_peer_connect.argtypes = [vp, vp]
+        L.p3d_mc_peer_destroy.restype = None
+        L.p3d_mc_peer_destroy.argtypes = [vp]
+        L.p3d_mc_sharded_extract_p2p.restype = ctypes.c_int
+        L.p3d_mc_sharded_extract_p2p.argtypes = [dp, vp, ctypes.c_int, vp, sz, vp, vp, i64, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_extract_sparse.restype = ctypes.c_int
         L.p3d_mc_extract_sparse.argtypes = [dp, vp, ctypes.c_int, vp, i64, vp, sz, vp, i64, vp, i64, ctypes.POINTER(i64), vp]
         L.p3d_mc_extract_host.restype = ctypes.c_int

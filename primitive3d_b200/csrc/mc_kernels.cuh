@@ -158,6 +158,19 @@ SmallWorkspace bind_small(void *base, int64_t nwords, int ngrids, SmallGrid **gr
 bool launch_small(const SmallBatch &b, const SmallGrid *grids_dev, const SmallWorkspace &ws, cudaStream_t s,
                   unsigned long long *totals_host);
 
+// ---- shard-boundary exchange over peer memory (mc_peer.cu) ----
+constexpr int kMaxPeers = 32;                 // ranks of one exchange (one NVLink domain)
+constexpr int kPeerDoneWord = 2 * kMaxPeers;  // control words of a mailbox: flags[2][kMaxPeers], done, timeout
+constexpr int kPeerTimeoutWord = kPeerDoneWord + 1;
+constexpr int kPeerDataOffset = 512;          // bytes: recv[2][world][n + 1] uint4 follow the control words
+struct PeerParams {
+    char *peer[kMaxPeers];  // every rank's mailbox, mapped into this process (peer[rank] = my own)
+    int rank, world;
+    long long n;            // table entries of a plane (ry * np)
+};
+void launch_export_p2p(const PeerParams &pp, const McWorkspace &ws, uint32_t epoch, cudaStream_t s);
+void launch_wait_p2p(char *own_base, int world, uint32_t epoch, cudaStream_t s);
+
 const char *tile_pass_error();  // non-null if the last launch_tile_pass could not build its TMA descriptor
 
 }  // namespace p3d

@@ -590,6 +590,109 @@ p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int
     return P3D_OK;
 }
 
+// ---- the same exchange over peer memory (mc_peer.cu): no collective between the two passes ----
+struct p3d_mc_peer {
+    int rank = 0, world = 1, device = 0;
+    int64_t n = 0;                        // table entries of a plane
+    size_t bytes = 0;
+    char *base = nullptr;                 // my mailbox (cudaMalloc)
+    char *peer[p3d::kMaxPeers] = {};      // every rank's mailbox as mapped here; peer[rank] = base
+    bool connected = false;
+    uint32_t epoch = 0;                   // calls made so far (the same on every rank: the call is collective)
+};
+
+size_t p3d_mc_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+p3d_status p3d_mc_peer_create(const p3d_mc_desc *desc, int rank, int world, p3d_mc_peer **out, void *handle_out) {
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || !out || !handle_out) return fail(P3D_ERR_INVALID, "p3d_mc_peer_create: invalid argument");
+    if (world < 1 || world > p3d::kMaxPeers || rank < 0 || rank >= world)
+        return fail(P3D_ERR_INVALID, "p3d_mc_peer_create: bad rank / world (at most " + std::to_string(p3d::kMaxPeers) + " ranks)");
+    p3d_mc_peer *p = new p3d_mc_peer();
+    p->rank = rank, p->world = world;
+    p->n = g.ry * (int64_t)g.np;
+    p->bytes = (size_t)p3d::kPeerDataOffset + (size_t)2 * world * (size_t)(p->n + 1) * 16;
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&p->base), p->bytes);
+    if (e == cudaSuccess) e = cudaMemset(p->base, 0, p->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->base);
+    if (e != cudaSuccess) {
+        if (p->base) cudaFree(p->base);
+        delete p;
+        return fail(P3D_ERR_CUDA, std::string("p3d_mc_peer_create: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof h);
+    p->peer[rank] = p->base;
+    *out = p;
+    return P3D_OK;
+}
+
+p3d_status p3d_mc_peer_connect(p3d_mc_peer *p, const void *handles) {
+    if (!p || !handles) return fail(P3D_ERR_INVALID, "p3d_mc_peer_connect: null pointer");
+    if (p->connected) return P3D_OK;
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int t = 0; t < p->world; ++t) {
+        if (t == p->rank) continue;
+        void *q = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&q, h[t], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(P3D_ERR_CUDA, "p3d_mc_peer_connect: cudaIpcOpenMemHandle of rank " + std::to_string(t) + " failed: " + cudaGetErrorString(e));
+        p->peer[t] = static_cast<char *>(q);
+    }
+    p->connected = true;
+    return P3D_OK;
+}
+
+void p3d_mc_peer_destroy(p3d_mc_peer *p) {
+    if (!p) return;
+    for (int t = 0; t < p->world; ++t)
+        if (t != p->rank && p->peer[t]) cudaIpcCloseMemHandle(p->peer[t]);
+    if (p->base) cudaFree(p->base);
+    delete p;
+}
+
+p3d_status p3d_mc_sharded_extract_p2p(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace, size_t workspace_bytes,
+                                      p3d_mc_peer *peer, float *vertices, int64_t vertex_capacity, int32_t *faces,
+                                      int64_t face_capacity, int64_t *counts_host, void *stream) {
+    if (!peer || !counts_host) return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract_p2p: null pointer");
+    if (!peer->connected && peer->world > 1) return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract_p2p: p3d_mc_peer_connect has not been called");
+    p3d::McGeom g;
+    if (!make_geom(desc, &g) || g.ry * (int64_t)g.np != peer->n)
+        return fail(P3D_ERR_INVALID, "p3d_mc_sharded_extract_p2p: the descriptor's plane does not match the mailbox");
+    const int rank = peer->rank, world = peer->world;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    p3d_status st = p3d_mc_tile_async(desc, grid, dtype, workspace, workspace_bytes, vertices, vertex_capacity, stream);
+    if (st != P3D_OK) return st;
+    const uint32_t epoch = ++peer->epoch;
+    p3d::PeerParams pp;
+    for (int t = 0; t < p3d::kMaxPeers; ++t) pp.peer[t] = peer->peer[t];
+    pp.rank = rank, pp.world = world, pp.n = peer->n;
+    p3d::launch_export_p2p(pp, bind(workspace, make_layout(g)), epoch, s);
+    p3d::launch_wait_p2p(peer->base, world, epoch, s);
+    P3D_CUDA(cudaGetLastError());
+    const int64_t words = 4 * (peer->n + 1);
+    const uint32_t *recv = reinterpret_cast<const uint32_t *>(peer->base + p3d::kPeerDataOffset) + (size_t)(epoch & 1u) * world * words;
+    st = p3d_mc_faces_exchanged(desc, workspace, recv, rank, world, faces, face_capacity, stream);
+    if (st != P3D_OK) return st;
+    // every shard's {V, F} (the last four words of its slot) and the timeout word: one wait
+    int64_t *pin = pinned_counts((size_t)world + 1);
+    if (!pin) return fail(P3D_ERR_CUDA, "p3d_mc_sharded_extract_p2p: pinned allocation failed");
+    P3D_CUDA(cudaMemcpy2DAsync(pin, 16, recv + (words - 4), (size_t)words * 4, 16, (size_t)world, cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaMemcpyAsync(pin + 2 * world, reinterpret_cast<const unsigned int *>(peer->base) + p3d::kPeerTimeoutWord, 4,
+                             cudaMemcpyDeviceToHost, s));
+    P3D_CUDA(cudaStreamSynchronize(s));
+    if (*reinterpret_cast<const uint32_t *>(pin + 2 * world) != 0u)
+        return fail(P3D_ERR_CUDA, "p3d_mc_sharded_extract_p2p: a peer did not deliver its payload (timeout in the exchange)");
+    int64_t total_v = 0;
+    for (int i = 0; i < 2 * world; ++i) counts_host[i] = pin[i];
+    for (int r = 0; r < world; ++r) total_v += counts_host[2 * r];
+    if (total_v > INT32_MAX)
+        return fail(P3D_ERR_OVERFLOW, "p3d_mc_sharded_extract_p2p: global vertex count exceeds the int32 face-index contract");
+    return P3D_OK;
+}
+
 p3d_status p3d_mc_debug_stage(const p3d_mc_desc *desc, const float *grid, void *workspace, int stage, float *vertices,
                               int64_t vertex_capacity, void *stream) {
     p3d::McGeom g;

@@ -340,6 +340,83 @@ def nccl_comm_destroy(comm):
     nccl.ncclCommDestroy(ctypes.c_void_p(comm))
 
 
+class PeerExchange:
+    """This rank's mailbox for the shard-boundary exchange over peer memory (p3d_mc_peer_*): created collectively by
+    every rank of `group` for shards whose planes are ry x rz; the IPC handles travel through one all-gather of
+    torch.distributed (set-up only: the extraction calls that follow make no collective call).  close() is collective."""
+
+    def __init__(self, ry, rz, thresh=0.0, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = capi.lib()
+        desc = capi.McDesc.make((8, int(ry), int(rz)), thresh)   # only the plane matters
+        nbytes = L.p3d_mc_peer_handle_bytes()
+        mine = (ctypes.c_ubyte * nbytes)()
+        self.ptr = ctypes.c_void_p()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        with capi._on_device(dev):
+            capi.check(L.p3d_mc_peer_create(ctypes.byref(desc), self.rank, self.world, ctypes.byref(self.ptr), mine))
+        send = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).to(dev)
+        recv = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        handles = recv.cpu().numpy().tobytes()
+        with capi._on_device(dev):
+            capi.check(L.p3d_mc_peer_connect(self.ptr, handles))
+        dist.barrier(group=group)   # every rank has mapped every mailbox before anybody stores into one
+        self.plane = (int(ry), int(rz))
+
+    def close(self):
+        if self.ptr:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)   # nobody is inside a call any more
+            capi.lib().p3d_mc_peer_destroy(self.ptr)
+            self.ptr = ctypes.c_void_p()
+
+
+def marching_cubes_slab_p2p(slab, thresh, x_begin, global_rx, peer, vertex_capacity=None, face_capacity=None):
+    """marching_cubes_slab through ONE C call with the exchange over peer memory (p3d_mc_sharded_extract_p2p): tile
+    pass, NVLink stores into the neighbours' mailboxes, a flag wait, face pass; no NCCL call.  Collective over the
+    ranks of `peer` (a PeerExchange for this plane size)."""
+    rank, world = peer.rank, peer.world
+    x0, x1 = slab_range(global_rx, world, rank)
+    if x0 != x_begin or slab.shape[0] != min(x1 + 1, global_rx) - x0:
+        raise ValueError(f"rank {rank}: slab must hold planes [{x0}, {min(x1 + 1, global_rx)})")
+    ry, rz = slab.shape[1], slab.shape[2]
+    if (ry, rz) != peer.plane:
+        raise ValueError("the PeerExchange was made for another plane size")
+    desc = capi.McDesc.make(slab.shape, thresh, [0.0, 0.0, 0.0], [float(global_rx), float(ry), float(rz)], owned_x=x1 - x0,
+                            x_origin=x0, global_rx=global_rx)
+    L = capi.lib()
+    dev = slab.device
+    ws_bytes, hint = capi._desc_sizes(desc)
+    key = tuple(int(s) for s in slab.shape)
+    if vertex_capacity is None:
+        vertex_capacity = capacity_for(slab.shape)
+    vertex_capacity = hint if vertex_capacity is None else int(vertex_capacity)
+    if face_capacity is None:
+        f_prev = _last_face_count.get(key)
+        face_capacity = 2 * vertex_capacity if f_prev is None else f_prev + f_prev // 16 + 4096
+    face_capacity = int(face_capacity)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    vbuf = torch.empty((vertex_capacity, 3), dtype=torch.float32, device=dev)
+    fbuf = torch.empty((face_capacity, 3), dtype=torch.int32, device=dev)
+    counts = (ctypes.c_int64 * (2 * world))()
+    with capi._on_device(dev):
+        capi.check(L.p3d_mc_sharded_extract_p2p(ctypes.byref(desc), slab.data_ptr(), capi._grid_ok(slab), ws.data_ptr(), ws.numel(),
+                                                peer.ptr, vbuf.data_ptr(), vertex_capacity, fbuf.data_ptr(), face_capacity, counts,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    pairs = [(counts[2 * r], counts[2 * r + 1]) for r in range(world)]
+    V, F = pairs[rank]
+    if len(_last_vertex_count) > 64:
+        _last_vertex_count.clear()
+        _last_face_count.clear()
+    _last_vertex_count[key], _last_face_count[key] = V, F
+    v_off, f_off, v_tot, f_tot = exclusive_offsets(pairs, rank)
+    verts = capi.mc_vertices(desc, slab, ws, V, vbuf)
+    faces = fbuf[:F] if F <= face_capacity else capi.mc_faces(desc, ws, F, v_off)
+    return SlabMesh(verts, faces, v_off, f_off, v_tot, f_tot)
+
+
 def marching_cubes_slab_c(slab, thresh, x_begin, global_rx, comm, rank, world, vertex_capacity=None, face_capacity=None):
     """marching_cubes_slab through ONE C call (p3d_mc_sharded_extract) over the raw communicator `comm`."""
     x0, x1 = slab_range(global_rx, world, rank)

@@ -22,7 +22,8 @@ def test_header_declares_the_expected_entry_points():
     for s in ["p3d_mc_workspace_bytes", "p3d_mc_vertex_capacity_hint", "p3d_mc_count", "p3d_mc_vertices", "p3d_mc_faces",
               "p3d_mc_count_typed", "p3d_mc_vertices_typed", "p3d_mc_extract", "p3d_mc_extract_sparse", "p3d_mc_extract_batch", "p3d_mc_batch_workspace_bytes", "p3d_mc_extract_host",
               "p3d_mc_extract_host_arena_bytes", "p3d_mc_tile_async", "p3d_mc_exchange_words", "p3d_mc_export_exchange",
-              "p3d_mc_faces_exchanged", "p3d_mc_sharded_extract", "p3d_ply_pack",
+              "p3d_mc_faces_exchanged", "p3d_mc_sharded_extract", "p3d_mc_sharded_extract_p2p", "p3d_mc_peer_create",
+              "p3d_mc_peer_connect", "p3d_mc_peer_destroy", "p3d_mc_peer_handle_bytes", "p3d_ply_pack",
               "p3d_mc_run", "p3d_mc_plane_table_words", "p3d_mc_export_first_plane",
               "p3d_mc_import_halo_plane", "p3d_mt_classify", "p3d_mt_index", "p3d_mt_emit", "p3d_mt_backward", "p3d_mt_extract",
               "p3d_mt_extract_workspace_bytes",
@@ -35,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(lib, s), f"{s} declared in include/prim3d_b200.h but not exported"
-    assert capi.abi_version() == 4
+    assert capi.abi_version() == 5
 
 
 def test_workspace_size_is_a_few_bits_per_sample():

@@ -36,6 +36,17 @@ def main():
         (out.v_offset, out.f_offset, out.num_vertices_total, out.num_faces_total)
     assert torch.equal(out_c.vertices.view(torch.int32), out.vertices.view(torch.int32)) and torch.equal(out_c.faces, out.faces)
     sharded.nccl_comm_destroy(comm)
+    # ... and with the exchange over peer memory (p3d_mc_sharded_extract_p2p: no collective between the passes),
+    # several calls in a row (the mailbox alternates between two buffers)
+    peer = sharded.PeerExchange(n, n)
+    for it in range(5):
+        out_p = sharded.marching_cubes_slab_p2p(slab, 0.0, x0, n, peer)
+        torch.cuda.synchronize()
+        assert (out_p.v_offset, out_p.f_offset, out_p.num_vertices_total, out_p.num_faces_total) == \
+            (out.v_offset, out.f_offset, out.num_vertices_total, out.num_faces_total), f"p2p call {it}: offsets differ"
+        assert torch.equal(out_p.vertices.view(torch.int32), out.vertices.view(torch.int32)) and torch.equal(out_p.faces, out.faces), \
+            f"p2p call {it}: mesh differs"
+    peer.close()
     # numbering-independent checksums of the sharded mesh (primitive3d_b200/verify.py), taken shard-wise
     from primitive3d_b200 import verify
     sums = verify.mesh_checksums(out.vertices, out.faces, out.v_offset, out.f_offset, float(x0))
@@ -59,7 +70,7 @@ def main():
         assert torch.equal(fs, f.cpu()), "faces differ"
         assert verify.mesh_checksums(v, f, single=True) == sums, "checksums of the sharded and the single-GPU mesh differ"
         print(f"sharded NCCL check OK: world={world} n={n} V={v.shape[0]} F={f.shape[0]} "
-              f"(python driver == p3d_mc_sharded_extract == host-pipelined shards == single GPU; checksums {sums[0]:016x} {sums[1]:016x})")
+              f"(python driver == p3d_mc_sharded_extract == p3d_mc_sharded_extract_p2p == host-pipelined shards == single GPU; checksums {sums[0]:016x} {sums[1]:016x})")
     dist.barrier()
     dist.destroy_process_group()
 

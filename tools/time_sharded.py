@@ -1,6 +1,7 @@
-"""Times the two multi-GPU drivers of the sharded extraction on the bench workload (gyroid N^3, dim-0 slabs):
-sharded.marching_cubes_slab (python, torch.distributed all-gather) and sharded.marching_cubes_slab_c (the single C entry
-p3d_mc_sharded_extract over a raw NCCL communicator).  Launch with torch.distributed.run, one rank per GPU.
+"""Times the multi-GPU drivers of the sharded extraction on the bench workload (gyroid N^3, dim-0 slabs):
+sharded.marching_cubes_slab (python, torch.distributed all-gather), sharded.marching_cubes_slab_c (the single C entry
+p3d_mc_sharded_extract over a raw NCCL communicator) and sharded.marching_cubes_slab_p2p (the same with the exchange over
+peer memory, p3d_mc_sharded_extract_p2p).  Launch with torch.distributed.run, one rank per GPU.
   python -m torch.distributed.run --nproc-per-node N ... tools/time_sharded.py [size] [steps]"""
 import os
 import sys
@@ -46,7 +47,13 @@ def timed(fn):
 
 t_py = timed(lambda: sharded.marching_cubes_slab(slab, 0.0, x0, n))
 t_c = timed(lambda: sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world, caps[0], caps[1]))
+peer = sharded.PeerExchange(slab.shape[1], slab.shape[2])
+t_p = timed(lambda: sharded.marching_cubes_slab_p2p(slab, 0.0, x0, n, peer, caps[0], caps[1]))
+t_c2 = timed(lambda: sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world, caps[0], caps[1]))
+t_p2 = timed(lambda: sharded.marching_cubes_slab_p2p(slab, 0.0, x0, n, peer, caps[0], caps[1]))
 if rank == 0:
-    print(f"world={world} n={n}: python driver {t_py:.4f} ms/step, C entry {t_c:.4f} ms/step")
+    print(f"world={world} n={n}: python driver {t_py:.4f} ms/step, C entry (ncclAllGather) {t_c:.4f} / {t_c2:.4f} ms/step, "
+          f"C entry (peer memory) {t_p:.4f} / {t_p2:.4f} ms/step")
+peer.close()
 sharded.nccl_comm_destroy(comm)
 dist.destroy_process_group()
