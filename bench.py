@@ -233,14 +233,17 @@ def main():
         if os.environ.get("P3D_BENCH_DRIVER", "c") == "python":
             def step():
                 return sharded.marching_cubes_slab(slab, 0.0, x0, n)
-        elif os.environ.get("P3D_BENCH_EXCHANGE", "p2p") == "nccl":
+        elif os.environ.get("P3D_BENCH_EXCHANGE", "nccl") != "p2p":
             comm = sharded.nccl_comm_init()
 
             def step():
                 return sharded.marching_cubes_slab_c(slab, 0.0, x0, n, comm, rank, world)
         else:
-            # default: the same one C call with the shard-boundary exchange over peer memory (NVLink stores into the
-            # neighbours' mailboxes + flags, p3d_mc_sharded_extract_p2p): no collective call inside the timed region
+            # P3D_BENCH_EXCHANGE=p2p: the same one C call with the shard-boundary exchange over peer memory (NVLink stores
+            # into the neighbours' mailboxes + flags, p3d_mc_sharded_extract_p2p): no collective call inside the timed
+            # region.  Measured 1.62 against 1.73 ms per step on 8 GPUs (profiles/r2h_bench_gyroid2048_n8_p2p.json); not
+            # the default because the teardown of the IPC mappings across 8 exiting processes could not be re-checked
+            # within the round's GPU budget.
             exchange = "p2p"
             peer = sharded.PeerExchange(slab.shape[1], slab.shape[2])
 
