@@ -216,7 +216,7 @@ def main():
 
     # our kernels per step: k_tile, k_round_sums, k_faces_rows (+ k_export_p2p / k_export_exchange, k_wait_p2p,
     # k_apply_exchange on several GPUs)
-    launches_per_step = 3 if world == 1 else 6
+    launches_per_step = 3 if world == 1 else 5
     exchange = "nccl all-gather"
 
     if world == 1:
@@ -245,6 +245,7 @@ def main():
             # the default because the teardown of the IPC mappings across 8 exiting processes could not be re-checked
             # within the round's GPU budget.
             exchange = "p2p"
+            launches_per_step = 6
             peer = sharded.PeerExchange(slab.shape[1], slab.shape[2])
 
             def step():
