@@ -255,12 +255,16 @@ p3d_status p3d_mc_sharded_extract(const p3d_mc_desc *desc, const void *grid, int
  *   p3d_mc_sharded_extract_p2p   arguments and results as p3d_mc_sharded_extract; COLLECTIVE: every rank of the
  *                         mailbox makes the same sequence of calls (a rank that never arrives ends the others' wait
  *                         with P3D_ERR_CUDA after a few seconds instead of hanging the device);
- *   p3d_mc_peer_destroy   after a barrier of the caller's: no rank may still be inside a call.
+ *   p3d_mc_peer_disconnect  unmaps the other ranks' mailboxes (after a barrier of the caller's: no rank may still be
+ *                         inside a call);
+ *   p3d_mc_peer_destroy   disconnects if that has not been done, and frees this rank's mailbox.  A mailbox should not
+ *                         be freed while another process still maps it: disconnect on every rank, barrier, destroy.
  * One process per GPU (IPC handles cannot be opened by the process that made them); at most 32 ranks. */
 typedef struct p3d_mc_peer p3d_mc_peer;
 size_t p3d_mc_peer_handle_bytes(void);
 p3d_status p3d_mc_peer_create(const p3d_mc_desc *desc, int rank, int world, p3d_mc_peer **out, void *handle_out);
 p3d_status p3d_mc_peer_connect(p3d_mc_peer *peer, const void *handles);
+void p3d_mc_peer_disconnect(p3d_mc_peer *peer);
 void p3d_mc_peer_destroy(p3d_mc_peer *peer);
 p3d_status p3d_mc_sharded_extract_p2p(const p3d_mc_desc *desc, const void *grid, int dtype, void *workspace,
                                       size_t workspace_bytes, p3d_mc_peer *peer, float *vertices, int64_t vertex_capacity,

@@ -82,6 +82,8 @@ def lib():
         L.p3d_mc_peer_create.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), vp]
         L.p3d_mc_peer_connect.restype = ctypes.c_int
         L.p3d_mc_peer_connect.argtypes = [vp, vp]
+        L.p3d_mc_peer_disconnect.restype = None
+        L.p3d_mc_peer_disconnect.argtypes = [vp]
         L.p3d_mc_peer_destroy.restype = None
         L.p3d_mc_peer_destroy.argtypes = [vp]
         L.p3d_mc_sharded_extract_p2p.restype = ctypes.c_int

@@ -645,10 +645,19 @@ p3d_status p3d_mc_peer_connect(p3d_mc_peer *p, const void *handles) {
     return P3D_OK;
 }
 
-void p3d_mc_peer_destroy(p3d_mc_peer *p) {
+void p3d_mc_peer_disconnect(p3d_mc_peer *p) {
     if (!p) return;
     for (int t = 0; t < p->world; ++t)
-        if (t != p->rank && p->peer[t]) cudaIpcCloseMemHandle(p->peer[t]);
+        if (t != p->rank && p->peer[t]) {
+            cudaIpcCloseMemHandle(p->peer[t]);
+            p->peer[t] = nullptr;
+        }
+    p->connected = false;
+}
+
+void p3d_mc_peer_destroy(p3d_mc_peer *p) {
+    if (!p) return;
+    p3d_mc_peer_disconnect(p);
     if (p->base) cudaFree(p->base);
     delete p;
 }

@@ -369,6 +369,9 @@ class PeerExchange:
         if self.ptr:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)   # nobody is inside a call any more
+            capi.lib().p3d_mc_peer_disconnect(self.ptr)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)   # nobody maps anybody's mailbox any more: now they can be freed
             capi.lib().p3d_mc_peer_destroy(self.ptr)
             self.ptr = ctypes.c_void_p()
 
