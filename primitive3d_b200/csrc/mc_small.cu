@@ -5,14 +5,15 @@
 // by bandwidth.  The reference's TODO for this regime is marching_cubes.cu:255-256.  Citations below are into
 // /root/reference/src/prim3d/Utility/marching_cubes.cu.
 //
-// One persistent kernel, every CTA resident, three phases separated by a device-wide barrier.  The unit of work is a
-// bit word = 32 consecutive samples of a row, and a WARP takes a word: lane i is sample / cell i of the word, so every
-// load is one coalesced 128-byte row segment, every mask is a ballot, and nothing in the kernel is a per-thread loop
-// over the bits of a mask (the previous form, a thread per word, spent its 39 us at bunny 66^3 in those serial loops
-// on 52 CTAs).
-//   1  inside bits of the four rows a word's cells touch (value > thresh, :25): four loads and four ballots; crossing
-//      masks, vertex counts (:29-45) and triangle counts (:48-66: a lane looks up its cell's case, one warp reduction)
-//      per word, packed into one 32-bit count word; CTA totals
+// One persistent kernel (a cooperative launch: every CTA resident), three phases separated by a device-wide barrier.
+// The unit of work is a bit word = 32 consecutive samples of a row, and a WARP takes a group of 2..32 consecutive words:
+// lane j owns word j of the group (where it sits, its masks and counts, what it needs from the workspace), and the 32
+// lanes together do the sample-level work of each word in turn, lane i = sample / cell i: every load is one coalesced
+// 128-byte row segment, every mask is a ballot (the first form of this kernel, a thread per word with per-thread
+// loops over 128 samples and over the bits of its masks, took 39 us at bunny 66^3 on 52 CTAs; this one 22 us).
+//   1  inside bits of the four rows a word's cells touch (value > thresh, :25): four loads and four ballots per word;
+//      crossing masks, vertex counts (:29-45) and triangle counts (:48-66: the owner looks up the cells with mixed
+//      corners) per word, packed into one 32-bit count word; CTA totals
 //   2  exclusive prefix over the words (CTA totals -> per-word first vertex id / first face index, numbering restarts
 //      at every grid), a thread per word
 //   3  vertices of the word's own +x / +y / +z edges, a lane per sample, interpolated in the reference's fp32 order
